@@ -1,0 +1,141 @@
+/*
+ * nddwt_b200.h -- C ABI of the B200-native non-decimated wavelet library (libnddwt_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of arg-min-x/Non-Decimated_Wavelets:
+ * it replaces mex/nddwt.h (the native core behind nd_dwt_mex) and the parts of the MATLAB
+ * classes that build and apply the stored filters.  Plain C: pointers, sizes, int return codes.
+ * All arrays are dense COLUMN-MAJOR (MATLAB order, dim 1 contiguous); complex numbers are
+ * interleaved (re, im) pairs.  The coefficient stack is [dims..., nb] with
+ * nb = 1 + level*(2^ndims - 1) bands, deepest level first (mex/nddwt.c:209-210,226;
+ * mex/nd_dwt_mex.c:79-83): slot 0 = a_J, slots 1..2^d-1 = d_J, ..., last 2^d-1 = d_1;
+ * band b = sum_i b_i 2^(i-1), b_i = 1 for the high-pass along dim i.
+ *
+ * Every function returns 0 on success or a negative nddwt_status; nddwt_last_error() returns
+ * the message of the calling thread's last failure.  There is no CPU path: every entry point
+ * that computes needs a CUDA device and fails with NDDWT_ERR_CUDA without one.
+ */
+#ifndef NDDWT_B200_H
+#define NDDWT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define NDDWT_API __attribute__((visibility("default")))
+#else
+#define NDDWT_API
+#endif
+
+#define NDDWT_MAX_DIMS 4
+#define NDDWT_MAX_LEVELS 16
+
+typedef struct nddwt_plan nddwt_plan;
+
+/* element types: the reference's 'precision' x real/complex (nd_dwt_1D.m:124-126,144-148) */
+typedef enum {
+    NDDWT_F32 = 0,   /* real single    */
+    NDDWT_F64 = 1,   /* real double    */
+    NDDWT_C64 = 2,   /* complex single */
+    NDDWT_C128 = 3   /* complex double */
+} nddwt_dtype;
+
+typedef enum {
+    NDDWT_OK = 0,
+    NDDWT_ERR_ARG = -1,       /* bad argument (sizes, level, dtype, null pointer) */
+    NDDWT_ERR_WAVELET = -2,   /* "Unknown Wavelet Name"           (wave_filters.m:158-159) */
+    NDDWT_ERR_SHORT_DIM = -3, /* data dim shorter than the filter (nd_dwt_2D.m:271-277)     */
+    NDDWT_ERR_CUDA = -4,      /* CUDA runtime failure / no device */
+    NDDWT_ERR_NOMEM = -5,
+    NDDWT_ERR_SIZE = -6       /* "FIlter size and image size not consistant" (nd_dwt_mex.c:36-51,124-127) */
+} nddwt_status;
+
+NDDWT_API const char *nddwt_last_error(void);
+NDDWT_API const char *nddwt_version(void);
+
+/* [low_d, hi_d] = wave_filters(wname)   -- replaces Functions/wave_filters.m:1-174.
+ * Writes *len taps (2..20) into low_d and hi_d (each must hold 20 doubles). */
+NDDWT_API int nddwt_wave_filters(const char *wname, double *low_d, double *hi_d, int *len);
+
+/* nb = 2^d + (2^d - 1)(level - 1)       -- mex/nd_dwt_mex.c:83 */
+NDDWT_API int64_t nddwt_num_bands(int ndims, int level);
+/* level from the band count             -- nd_dwt_1D.m:213, nd_dwt_2D.m:215, nd_dwt_3D.m:217, nd_dwt_4D.m:213.
+ * Returns 0 when nb matches no level. */
+NDDWT_API int nddwt_infer_level(int ndims, int64_t nb);
+
+/* Plan = the "stored filter" object: replaces the constructor + get_filters of
+ * nd_dwt_{1,2,3,4}D.m (nd_dwt_1D.m:79-133,257-290 ... nd_dwt_4D.m:79-134,255-391) and
+ * init_fftw_plan (mex/nddwt.c:15-61).  Holds per-dim taps (device-ready), scratch for the
+ * intermediate approximation bands, and is reused across any number of dec/rec calls.
+ *   ndims    1..4;  dims[ndims] sizes in MATLAB order
+ *   wnames   ndims strings "db1".."db10" (one per dim; harr_nddwt_* == "db1")
+ *   dtype    nddwt_dtype of x and of the coefficients
+ *   pres_l2_norm  0/1: scale 2^(-d/2) per level so that ||coeffs|| = ||x|| (nd_dwt_2D.m:295-299)
+ *   device   CUDA device ordinal */
+NDDWT_API int nddwt_plan_create(nddwt_plan **plan, int ndims, const int64_t *dims,
+                      const char *const *wnames, int dtype, int pres_l2_norm, int device);
+NDDWT_API int nddwt_plan_destroy(nddwt_plan *plan);
+
+/* Opt-in a-trous mode: dilation of the taps at level j (1-based) is dil[j-1].  Default (and
+ * reference parity, nd_dwt_2D.m:183 / nddwt.c:214-228): 1 at every level. */
+NDDWT_API int nddwt_plan_set_dilations(nddwt_plan *plan, const int *dil, int nlevels);
+
+/* Selects the kernel family: 0 = auto (fused kernels where an instantiation exists, generic
+ * otherwise), 1 = force the generic separable kernels.  Both run on the GPU. */
+NDDWT_API int nddwt_plan_set_kernel_mode(nddwt_plan *plan, int mode);
+/* Number of kernel launches issued by the plan so far (bench.py's gpu_launches). */
+NDDWT_API int64_t nddwt_plan_launch_count(const nddwt_plan *plan);
+/* 1 if the last dec/rec of this plan ran the fused kernels, 0 if the generic ones. */
+NDDWT_API int nddwt_plan_last_path(const nddwt_plan *plan);
+
+/* y = dec(x, level)   -- replaces nd_dwt_dec / nd_dwt_dec_1level (mex/nddwt.c:98-139,189-239)
+ *                        together with the fftn the MATLAB side does first (nd_dwt_2D.m:156).
+ * x_dev: prod(dims) elements; coeffs_dev: prod(dims)*nb elements; both DEVICE pointers on the
+ * plan's device.  Asynchronous on `stream` (a cudaStream_t, may be NULL).  x is never written. */
+NDDWT_API int nddwt_dec(nddwt_plan *plan, const void *x_dev, void *coeffs_dev, int level, void *stream);
+
+/* x = rec(y)          -- replaces nd_dwt_rec / nd_dwt_rec_1level (mex/nddwt.c:142-186,242-292).
+ * Unlike the reference (nddwt.c:163,264-265) the coefficient stack is never modified. */
+NDDWT_API int nddwt_rec(nddwt_plan *plan, const void *coeffs_dev, void *x_dev, int level, void *stream);
+
+/* Same two calls with HOST buffers: the shape of nd_dwt_mex(x, f, dir, level, pres_l2)
+ * (mex/nd_dwt_mex.c:8-153) for host mxArrays.  Copies in, runs the kernels, copies out;
+ * synchronous.  Host memory may be pageable or pinned. */
+NDDWT_API int nddwt_dec_host(nddwt_plan *plan, const void *x_host, void *coeffs_host, int level);
+NDDWT_API int nddwt_rec_host(nddwt_plan *plan, const void *coeffs_host, void *x_host, int level);
+
+/* ---- slab interface (multi-GPU: one process per GPU, slabs along the LAST dimension) ----
+ * A slab plan is created with nddwt_plan_create_slab: local_dims[ndims-1] = number of LOCAL planes,
+ * global_last_dim = the full extent of that dimension (the filter-length check of
+ * nd_dwt_2D.m:271-277 applies to the global extent; a slab may be thinner than the filter).  One level of analysis of
+ * the local planes needs (L/2 - 1)*dil planes below and (L/2)*dil planes above the slab
+ * (L = taps of the last dim); the caller supplies them (neighbour exchange) as two dense
+ * buffers.  halo_lo holds the planes immediately below the slab in ascending order, halo_hi the
+ * planes immediately above.  Passing NULL for both means "periodic within the slab" (1 GPU). */
+NDDWT_API int nddwt_plan_create_slab(nddwt_plan **plan, int ndims, const int64_t *local_dims, int64_t global_last_dim,
+                           const char *const *wnames, int dtype, int pres_l2_norm, int device);
+NDDWT_API int nddwt_halo_planes(const nddwt_plan *plan, int level_index /*1-based*/, int *below, int *above);
+
+/* One analysis level: a_in (local planes) -> 2^d bands.  out_bands[b] are 2^d device pointers,
+ * each to a dense local-slab-sized array. */
+NDDWT_API int nddwt_dec_level_slab(nddwt_plan *plan, int level_index, const void *a_in,
+                         const void *halo_lo, const void *halo_hi,
+                         void *const *out_bands, void *stream);
+
+/* One synthesis level, split at the slab dimension (the adjoint of the analysis exchange):
+ *  stage 1 (local):  u_lo/u_hi[local planes] = synthesis over dims 1..d-1 of the 2^d bands,
+ *                    summed over their band bits (no halo needed);
+ *  stage 2:          a_out = synthesis along the last dim from u_lo/u_hi, which needs
+ *                    (L/2)*dil planes of u below and (L/2 - 1)*dil above (halo buffers hold
+ *                    u_lo planes then u_hi planes, each group ascending). */
+NDDWT_API int nddwt_rec_level_slab_stage1(nddwt_plan *plan, int level_index, const void *const *in_bands,
+                                void *u_lo, void *u_hi, void *stream);
+NDDWT_API int nddwt_rec_level_slab_stage2(nddwt_plan *plan, int level_index, const void *u_lo, const void *u_hi,
+                                const void *halo_lo, const void *halo_hi, void *a_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDDWT_B200_H */

@@ -1,0 +1,188 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI
+(ctypes -> libnddwt_b200.so); the oracle (numpy restatement of the reference) is only the checker.
+Tolerances are BASELINE.json's: relative L2 <= 1e-5 single, <= 1e-12 double."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import nddwt_b200 as nd
+from oracle import nddwt_oracle as orc
+from conftest import TOL
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+CLS = {1: nd.nd_dwt_1D, 2: nd.nd_dwt_2D, 3: nd.nd_dwt_3D, 4: nd.nd_dwt_4D}
+
+
+def _prec(dt):
+    return "single" if np.dtype(dt) in (np.dtype(np.float32), np.dtype(np.complex64)) else "double"
+
+
+def _obj(sizes, wn, l2, prec, compute="mex", kernel_mode=0):
+    d = len(sizes)
+    w = wn if (d > 1 or isinstance(wn, str)) else wn[0]
+    o = CLS[d](w, list(sizes), "pres_l2_norm", int(l2), "precision", prec, "compute", compute)
+    o.set_kernel_mode(kernel_mode)
+    return o
+
+
+@pytest.mark.parametrize("kernel_mode", [0, 1], ids=["auto", "generic"])
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_fixtures(path, kernel_mode):
+    z = np.load(path)
+    wn = [str(s) for s in z["wname"]]
+    wn = wn[0] if len(wn) == 1 else wn
+    x, y, level, l2 = z["x"], z["y"], int(z["level"]), bool(z["pres_l2"])
+    prec = _prec(x.dtype)
+    o = _obj(x.shape, wn, l2, prec, kernel_mode=kernel_mode)
+    yg = o.dec(x, level)
+    assert yg.shape == y.shape and yg.dtype == y.dtype
+    assert orc.rel_l2(yg, y) <= TOL[prec]
+    xg = o.rec(y)
+    assert xg.dtype == x.dtype
+    assert orc.rel_l2(xg, x) <= TOL[prec]
+    assert orc.rel_l2(o.rec(yg), x) <= TOL[prec]
+
+
+# the reference's own test shapes (Test/nddwt{1,2,3,4}D_test.m:5-8, mex/mex_test.m:11,48,84,120,
+# SURVEY.md 8c) -- odd, non-power-of-two sizes and mixed wavelets included
+REF_SHAPES = [
+    ((54321,), "db1", 4, 0),
+    ((10000,), "db1", 3, 1),
+    ((264, 264), ["db1", "db3"], 1, 1),
+    ((129, 131), "db3", 2, 0),
+    ((164, 64, 40), ["db1", "db3", "db1"], 1, 1),
+    ((131, 128, 30), "db3", 2, 0),
+    ((64, 64, 20), ["db1", "db3", "db9"], 2, 0),
+    ((64, 64, 20, 10), ["db1", "db3", "db1", "db1"], 1, 1),
+    ((32, 32, 16, 16), ["db1", "db3", "db3", "db5"], 2, 0),
+    ((128, 68, 8, 8), "db3", 1, 0),
+    ((256, 256), "db4", 3, 0),                      # BASELINE configs[0]
+    ((256, 256), ["db1", "db4"], 2, 1),             # example_nd_dwt_2D.m:5-8 literal parameters
+    ((64, 48, 40), "db4", 3, 0),
+    ((32, 32, 24, 16), "db4", 3, 1),
+    ((4096,), "db8", 6, 0),
+    ((40, 36, 20, 12), "db1", 3, 0),
+]
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128", "float32", "float64"])
+@pytest.mark.parametrize("sizes,wn,level,l2", REF_SHAPES, ids=[("x".join(map(str, c[0])) + "_" + (c[1] if isinstance(c[1], str) else "mix") + "_J%d" % c[2]) for c in REF_SHAPES])
+def test_parity_vs_oracle(sizes, wn, level, l2, dtype):
+    prec = _prec(dtype)
+    if np.prod(sizes) > 300000 and dtype in ("float32", "float64") and len(sizes) == 4:
+        pytest.skip("covered by the complex cases")
+    x = orc.synth(sizes, dtype, 11)
+    o = _obj(sizes, wn, l2, prec)
+    y = o.dec(x, level)
+    yo = orc.dec_direct(x.astype(np.complex128 if np.iscomplexobj(x) else np.float64), wn, level, bool(l2))
+    assert y.dtype == np.dtype(dtype)
+    assert y.shape == yo.shape
+    assert orc.rel_l2(y, yo) <= TOL[prec]
+    xr = o.rec(y)
+    assert orc.rel_l2(xr, x) <= TOL[prec]                                   # P1
+    if l2:
+        assert abs(np.linalg.norm(y.ravel()) / np.linalg.norm(x.ravel()) - 1) < 10 * TOL[prec]   # P2
+    # rec of arbitrary (non-image) coefficients == adjoint per the oracle
+    c = orc.synth(yo.shape, dtype, 12)
+    xo = orc.rec_direct(c.astype(np.complex128 if np.iscomplexobj(c) else np.float64), wn, bool(l2))
+    assert orc.rel_l2(o.rec(c), xo) <= TOL[prec]
+
+
+@pytest.mark.parametrize("sizes,wn,level,l2", [((64, 48, 40), "db4", 3, 0), ((129, 131), "db3", 2, 1),
+                                                ((32, 32, 24, 16), "db4", 2, 0), ((4099,), "db8", 4, 0)])
+def test_fused_equals_generic(sizes, wn, level, l2):
+    x = orc.synth(sizes, np.complex64, 5)
+    a = _obj(sizes, wn, l2, "single", kernel_mode=0)
+    b = _obj(sizes, wn, l2, "single", kernel_mode=1)
+    ya, yb = a.dec(x, level), b.dec(x, level)
+    assert orc.rel_l2(ya, yb) <= 2e-6
+    assert orc.rel_l2(a.rec(ya), b.rec(ya)) <= 2e-6
+
+
+def test_matches_fft_mat_path_and_mex_flow():
+    """P3: same answer as the restated 'mat' FFT path and the MEX slot flow."""
+    x = orc.synth((48, 40, 24), np.complex128, 2)
+    o = _obj(x.shape, "db4", 0, "double")
+    y = o.dec(x, 3)
+    assert orc.rel_l2(y, orc.dec(x, "db4", 3)) <= 1e-12
+    assert orc.rel_l2(y, orc.dec_mex(x, "db4", 3)) <= 1e-12
+
+
+def test_haar_classes():
+    for l2 in (0, 1):
+        x = orc.synth((24, 18), np.complex128, 4)
+        h = nd.harr_nddwt_2D([24, 18], "pres_l2_norm", l2)
+        y = h.dec(x, 1)
+        assert orc.rel_l2(y, orc.haar_level_1_dec(x, bool(l2))) <= 1e-12
+        assert orc.rel_l2(h.rec(y), orc.haar_level_1_rec(y, bool(l2))) <= 1e-12
+        x4 = orc.synth((10, 8, 6, 8), np.complex64, 5)
+        h4 = nd.harr_nddwt_4D([10, 8, 6, 8], "pres_l2_norm", l2, "precision", "single")
+        y4 = h4.dec(x4, 1)
+        assert orc.rel_l2(y4, orc.haar_level_1_dec(x4.astype(np.complex128), bool(l2))) <= 1e-5
+        assert orc.rel_l2(h4.rec(y4), x4) <= 1e-5
+
+
+def test_device_resident_path_and_input_not_mutated():
+    import torch
+    x = orc.synth((40, 36, 20), np.complex64, 9)
+    o = nd.nd_dwt_3D("db4", [40, 36, 20], "precision", "single", "compute", "gpu")
+    xd = nd.to_device(x)
+    yd = o.dec(xd, 2)
+    assert isinstance(yd, torch.Tensor) and yd.is_cuda and tuple(yd.shape) == (40, 36, 20, 15)
+    y = nd.to_host(yd)
+    assert orc.rel_l2(y, orc.dec_direct(x.astype(np.complex128), "db4", 2)) <= 1e-5
+    ykeep = yd.clone()
+    xr = o.rec(yd)
+    assert torch.equal(yd, ykeep)          # unlike nddwt.c:163 the coefficients are not modified
+    assert orc.rel_l2(nd.to_host(xr), x) <= 1e-5
+    assert torch.equal(xd, nd.to_device(x))
+
+
+def test_nd_dwt_mex_entry():
+    x = orc.synth((32, 20), np.complex128, 1)
+    f = nd.FilterSpec(["db2", "db3"], [32, 20])
+    y = nd.nd_dwt_mex(x, f, 0, 2, 1)
+    assert y.shape == (32, 20, 7)
+    assert orc.rel_l2(y, orc.dec(x, ["db2", "db3"], 2, True)) <= 1e-12
+    assert orc.rel_l2(nd.nd_dwt_mex(y, f, 1, 2, 1), x) <= 1e-12
+
+
+def test_linearity_and_shift_equivariance_full_size():
+    """Size-independent properties at a BASELINE size (cfg3: 256^3 complex single, db4, 3 levels)."""
+    import torch
+    n = 256
+    o = nd.nd_dwt_3D("db4", [n, n, n], "precision", "single", "compute", "gpu")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    def rnd():
+        t = torch.randn((n, n, n, 2), generator=g, device="cuda", dtype=torch.float32)
+        return torch.view_as_complex(t).permute(2, 1, 0)
+    a, b = rnd(), rnd()
+    ya, yb = o.dec(a, 3), o.dec(b, 3)
+    yab = o.dec(a + 2 * b, 3)
+    num = torch.linalg.vector_norm(yab - (ya + 2 * yb)); den = torch.linalg.vector_norm(yab)
+    assert float(num / den) <= 1e-5
+    del yab, yb
+    # circular shift equivariance: dec(roll(a)) == roll(dec(a))
+    ys = o.dec(torch.roll(a, shifts=(3, 5, 7), dims=(0, 1, 2)), 3)
+    num = torch.linalg.vector_norm(ys - torch.roll(ya, shifts=(3, 5, 7), dims=(0, 1, 2)))
+    assert float(num / torch.linalg.vector_norm(ys)) <= 1e-5
+    del ys
+    xr = o.rec(ya)
+    assert float(torch.linalg.vector_norm(xr - a) / torch.linalg.vector_norm(a)) <= 1e-5
+    # energy: frame bound 2^d per level without pres_l2_norm is not Parseval; use pres_l2_norm object
+    o2 = nd.nd_dwt_3D("db4", [n, n, n], "precision", "single", "compute", "gpu", "pres_l2_norm", 1)
+    y2 = o2.dec(a, 3)
+    assert abs(float(torch.linalg.vector_norm(y2) / torch.linalg.vector_norm(a)) - 1) <= 1e-4
+
+
+def test_dilated_atrous_mode_opt_in():
+    x = orc.synth((64, 48), np.complex128, 3)
+    o = nd.nd_dwt_2D("db2", [64, 48])
+    o.set_dilations([1, 2, 4])
+    y = o.dec(x, 3)
+    assert orc.rel_l2(y, orc.dec_direct(x, "db2", 3, dilations=[1, 2, 4])) <= 1e-12
+    assert orc.rel_l2(o.rec(y), x) <= 1e-12

@@ -1,0 +1,98 @@
+"""CPU tests: the C-ABI library loads, exports every symbol include/nddwt_b200.h declares, and
+the host-side logic (taps, band arithmetic, argument checks, API option parsing) behaves like the
+reference.  No compute calls (there is no GPU here and the library has no CPU path)."""
+import ctypes
+import os
+import re
+import warnings
+
+import numpy as np
+import pytest
+
+import nddwt_b200 as nd
+from oracle import nddwt_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "nddwt_b200.h")).read()
+    declared = set(re.findall(r"NDDWT_API[^;(]*?\b(nddwt_\w+)\s*\(", hdr))
+    assert declared == set(nd._lib.SYMBOLS), declared ^ set(nd._lib.SYMBOLS)
+    L = ctypes.CDLL(nd.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_wave_filters_matches_oracle():
+    for p in range(1, 11):
+        lo, hi = nd.wave_filters("db%d" % p)
+        olo, ohi = orc.wave_filters("db%d" % p)
+        assert np.array_equal(lo, olo) and np.array_equal(hi, ohi)
+    lo, _ = nd.wave_filters("DB4")   # switch lower(wname), wave_filters.m:19
+    assert len(lo) == 8
+    with pytest.raises(ValueError, match="Unknown Wavelet Name"):
+        nd.wave_filters("haar")
+
+
+def test_band_arithmetic():
+    L = nd.lib()
+    for d in range(1, 5):
+        for lv in range(1, 7):
+            nb = L.nddwt_num_bands(d, lv)
+            assert nb == orc.num_bands(d, lv)
+            assert L.nddwt_infer_level(d, nb) == lv
+        assert L.nddwt_infer_level(d, (1 << d) + 1) == (2 if d == 1 else 0)
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    obj = nd.nd_dwt_2D("db2", [16, 16])
+    with pytest.raises(nd.NddwtError, match="no usable CUDA device"):
+        obj.dec(np.zeros((16, 16)), 1)
+
+
+def test_constructor_option_parsing_and_errors():
+    o = nd.nd_dwt_3D(["db1", "db3", "db1"], [164, 64, 40], "pres_l2_norm", 1, "compute", "gpu_off", "precision", "single")
+    assert (o.pres_l2_norm, o.compute, o.precision) == (1, "gpu_off", "single")
+    assert o.f_size == {"s1": 2, "s2": 6, "s3": 2}
+    o = nd.nd_dwt_2D("db4", [256, 256])
+    assert (o.pres_l2_norm, o.compute, o.precision, o.wname) == (0, "mat", "double", ["db4", "db4"])
+    with pytest.raises(ValueError, match="sizes vector must be length 2"):
+        nd.nd_dwt_2D("db1", [8, 8, 8])
+    with pytest.raises(ValueError, match="scalar"):
+        nd.nd_dwt_1D("db1", [8, 8])
+    with pytest.raises(ValueError, match="Must be a string"):
+        nd.nd_dwt_1D(["db1"], 64)
+    with pytest.raises(ValueError, match="filter names"):
+        nd.nd_dwt_3D(["db1", "db2"], [8, 8, 8])
+    with pytest.raises(ValueError, match="come in pairs"):
+        nd.nd_dwt_2D("db1", [8, 8], "pres_l2_norm")
+    with pytest.raises(ValueError, match="Dimension 2 of Data is shorter"):
+        nd.nd_dwt_2D(["db1", "db4"], [8, 6])
+    with pytest.raises(ValueError, match="Unknown Wavelet Name"):
+        nd.nd_dwt_2D("coif1", [8, 8])
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        nd.nd_dwt_1D("db1", 64, "perserve_l2_norm", 1)   # the misspelt key of example_nd_dwt_1D.m:14
+        assert any("Unknown optional input" in str(x.message) for x in w)
+    o4 = nd.nd_dwt_4D("db1", [8, 8, 8, 8], "method", "conv")
+    assert o4.method == "conv"
+
+
+def test_haar_level_check():
+    h = nd.harr_nddwt_2D([16, 16], "pres_l2_norm", 1)
+    assert h.scale == 0.5
+    with pytest.raises(ValueError, match="Only single level decomposition supported for Harr"):
+        h.dec(np.zeros((16, 16)), 2)
+    assert abs(nd.harr_nddwt_4D([4, 4, 4, 4]).scale - 1 / np.sqrt(2)) < 1e-16
+
+
+def test_rec_rejects_bad_band_count():
+    o = nd.nd_dwt_2D("db1", [8, 8])
+    with pytest.raises(ValueError, match="not consistant"):
+        o.rec(np.zeros((8, 8, 5)))
+    with pytest.raises(ValueError, match="not consistant"):
+        o.dec(np.zeros((8, 9)), 1)
