@@ -1,0 +1,336 @@
+#!/usr/bin/env python3
+"""bench.py -- dec+rec throughput of the non-decimated wavelet hot path on B200.
+
+One "step" = one `dec` (x -> coefficient stack, materialised in HBM) followed by one `rec`
+(coefficients -> x) of a synthetic array of the named workload.  Metric: Mvoxels/s = input
+voxels / t(dec+rec).  Prints ONE JSON line (see the task contract): `value` = device-resident
+throughput, `e2e` = the same pair through the host-buffer C-ABI calls (H2D/D2H inside the
+timed region), `roofline` for the dominant kernel, `cpu_baseline` = the reference's CPU path
+timed on this host on a bounded sample.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg4|cfg5|cfg2|...]
+  python bench.py --impl reference ...     # the reference's CPU implementation (oracle/_ref or port)
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (sizes, wavelet, levels, dtype)        BASELINE.json configs
+    "cfg1": ((256, 256), "db4", 3, "complex128"),
+    "cfg2": ((65536, 4096), "db8", 6, "complex64"),     # 1-D batch (signals along dim 1) -- extension
+    "cfg3": ((256, 256, 256), "db4", 3, "complex64"),
+    "cfg4": ((256, 256, 256, 32), "db4", 3, "complex64"),
+    "cfg4s8": ((256, 256, 256, 8), "db4", 3, "complex64"),   # one quarter of cfg4 along dim 4
+    "cfg5": ((192, 192, 64, 48), "db4", 3, "complex64"),
+    "cfg5haar": ((192, 192, 64, 48), "db1", 1, "complex64"),
+    "small3d": ((128, 128, 128), "db4", 3, "complex64"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index=0, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_reference_pair(sizes, wname, level, dtype, threads, budget_s=25.0):
+    """Time the reference's CPU path on a bounded sample of the workload.  Returns a dict."""
+    from oracle import nddwt_oracle as orc
+    from oracle import ref_mex
+    orc.set_fft_workers(threads)
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    d = len(sizes)
+    # bounded sample: shrink the slowest dims until ~2M voxels (a few seconds of FFT work per pair)
+    samp = list(sizes)
+    target = 2 ** 21
+    i = d - 1
+    while np.prod(samp) > target:
+        if samp[i] // 2 >= 16:
+            samp[i] //= 2
+        i = (i - 1) % d
+        if all(s // 2 < 16 for s in samp):
+            break
+    samp = tuple(samp)
+    nvox = int(np.prod(samp))
+    prec = "single" if dtype in ("complex64", "float32") else "double"
+    x = orc.synth(samp, dtype, 0)
+    results = {}
+    # (i) 'mat' path restated with scipy.fft (the only single-precision path the reference has)
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        y = orc.dec(x, wname, level, False, precision=prec)
+        xr = orc.rec(y, wname, False, precision=prec)
+        reps += 1
+        if time.perf_counter() - t0 > budget_s / 2 or reps >= 3:
+            break
+    t_mat = (time.perf_counter() - t0) / reps
+    results["port_mat"] = nvox / t_mat / 1e6
+    err = orc.rel_l2(xr, x)
+    # (ii) the reference's own nddwt.c (double complex only) + FFT stand-in, incl. the MATLAB-side FFTs
+    if ref_mex.available():
+        t0 = time.perf_counter()
+        y = ref_mex.dec(x.astype(np.complex128), wname, level, False)
+        ref_mex.rec(y, wname, False)
+        results["ref_mex_c128"] = nvox / (time.perf_counter() - t0) / 1e6
+    best_kind = max(results, key=results.get)
+    return {"value": results[best_kind], "unit": "Mvoxels/s", "cores": threads,
+            "kind": "reference" if best_kind == "ref_mex_c128" else "port",
+            "sample": "%s %s J%d %s, one dec+rec pair; port('mat' path, scipy.fft workers=%d)=%.3f Mvox/s%s; PR err %.1e"
+                      % ("x".join(map(str, samp)), wname, level, dtype, threads, results["port_mat"],
+                         ("; oracle/_ref nddwt.c c128=%.3f Mvox/s" % results["ref_mex_c128"]) if "ref_mex_c128" in results else "",
+                         err),
+            "all": results}
+
+
+def run_reference(args, wl_name, wl):
+    sizes, wname, level, dtype = wl
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = len(os.sched_getaffinity(0))
+    vals = []
+    t_all = time.perf_counter()
+    base = None
+    for i in range(args.warmup + args.steps):
+        base = cpu_reference_pair(sizes, wname, level, dtype, threads, budget_s=6.0)
+        if i >= args.warmup:
+            vals.append(base["value"])
+        if time.perf_counter() - t_all > 150:
+            break
+    v = float(np.mean(vals)) if vals else base["value"]
+    base["value"] = v
+    line = {"impl": "reference", "metric": "dec+rec Mvoxels/s", "value": v, "unit": "Mvoxels/s",
+            "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup, "ms_per_step": None,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c64",
+            "data": "synthetic", "config": {"workload": wl_name, "sizes": list(sizes), "wavelet": wname,
+                                            "levels": level, "elem": dtype},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": "Mvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--kernel-mode", type=int, default=0)
+    args = ap.parse_args()
+
+    wl_name = args.workload or ("cfg3" if args.gpus == 1 else "cfg4")
+    wl = WORKLOADS[wl_name]
+    if args.impl == "reference":
+        return run_reference(args, wl_name, wl)
+    if args.gpus > 1:
+        from bench_multi import run_multi   # slab-sharded path (one process per GPU)
+        return run_multi(args, wl_name, wl)
+
+    import torch
+    import nddwt_b200 as nd
+
+    sizes, wname, level, dtype = wl
+    d = len(sizes)
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU path)"
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    cls = {1: nd.nd_dwt_1D, 2: nd.nd_dwt_2D, 3: nd.nd_dwt_3D, 4: nd.nd_dwt_4D}[d]
+    prec = "single" if dtype in ("complex64", "float32") else "double"
+    obj = cls(wname, list(sizes), "precision", prec, "compute", "gpu")
+    obj.set_kernel_mode(args.kernel_mode)
+    nvox = int(np.prod(sizes))
+    esize = np.dtype(dtype).itemsize
+    nb = obj._num_bands(level)
+
+    # synthetic input generated on the device (seeded), MATLAB-shaped view of column-major memory
+    g = torch.Generator(device=dev).manual_seed(0)
+    tdt = {"complex64": torch.float32, "complex128": torch.float64}[dtype]
+    base = torch.randn(tuple(reversed(sizes)) + (2,), generator=g, device=dev, dtype=tdt)
+    x = torch.view_as_complex(base).permute(*reversed(range(d)))
+    plan = obj._plan(True, 0)
+    y_buf = torch.empty((nb,) + tuple(reversed(sizes)), dtype=x.dtype, device=dev)
+    x_out = torch.empty(tuple(reversed(sizes)), dtype=x.dtype, device=dev)
+    xbase = x.permute(*reversed(range(d)))
+    assert xbase.is_contiguous()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    split = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+
+    def step(timed=False):
+        if timed:
+            split[0].record()
+        plan.dec(xbase.data_ptr(), y_buf.data_ptr(), level, stream)
+        if timed:
+            split[1].record()
+        plan.rec(y_buf.data_ptr(), x_out.data_ptr(), level, stream)
+        if timed:
+            split[2].record()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    pr_err = float(torch.linalg.vector_norm(x_out - xbase) / torch.linalg.vector_norm(xbase))
+    step(timed=True)
+    torch.cuda.synchronize()
+    dec_ms, rec_ms = split[0].elapsed_time(split[1]), split[1].elapsed_time(split[2])
+
+    l0 = plan.launches
+    sampler = ClockSampler(0)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter()
+    for e0, e1 in evs:
+        e0.record()
+        step()
+        e1.record()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    launches = plan.launches - l0
+    ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    total_ms = evs[0][0].elapsed_time(evs[-1][1])
+    ms_per_step = total_ms / args.steps
+    value = nvox / (ms_per_step * 1e-3) / 1e6
+
+    # ---- dominant kernel: analysis level 1 (reads the band once, writes 2^d subbands) timed alone
+    peak, peak_src = peaks()
+    nd_b = 1 << d
+    bands = [y_buf[(nb - nd_b) + b] for b in range(nd_b)]
+    ptrs = [t.data_ptr() for t in bands]
+    for _ in range(3):
+        plan.dec_level_slab(1, xbase.data_ptr(), None, None, ptrs, stream)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    lk0 = plan.launches
+    for e0, e1 in kev:
+        e0.record()
+        plan.dec_level_slab(1, xbase.data_ptr(), None, None, ptrs, stream)
+        e1.record()
+    torch.cuda.synchronize()
+    k_launch = (plan.launches - lk0) / args.steps
+    k_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in kev]))
+    alg_bytes_level = (1 + nd_b) * nvox * esize
+    achieved = alg_bytes_level / (k_ms * 1e-3) / 1e9
+    pair_bytes = 2 * (1 + nb) * nvox * esize
+    pair_gbs = pair_bytes / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "analysis level (k_dec*_fused, %d launch(es))" % round(k_launch),
+                "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes_level, "peak_source": peak_src,
+                "pair_algorithmic_bytes": pair_bytes, "pair_achieved_gbs": pair_gbs, "pair_frac": pair_gbs / peak,
+                "fused": bool(plan.last_path)}
+
+    # ---- e2e: the same pair through the host-buffer entry points (nd_dwt_mex shape), pinned memory
+    e2e = None
+    if not args.no_e2e:
+        hx = torch.empty(tuple(reversed(sizes)), dtype=x.dtype, pin_memory=True)
+        hy = torch.empty((nb,) + tuple(reversed(sizes)), dtype=x.dtype, pin_memory=True)
+        hx.copy_(xbase)
+        hx_np = hx.numpy().T
+        hy_np = hy.numpy().T
+        hobj = cls(wname, list(sizes), "precision", prec, "compute", "mex")
+        hobj.set_kernel_mode(args.kernel_mode)
+        hx2 = torch.empty_like(hx)
+        hx2_np = hx2.numpy().T
+        for _ in range(2):
+            hobj.dec(hx_np, level, out=hy_np)
+            hobj.rec(hy_np, out=hx2_np)
+        n_e2e = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            hobj.dec(hx_np, level, out=hy_np)
+            hobj.rec(hy_np, out=hx2_np)
+        t_e2e = (time.perf_counter() - t0) / n_e2e
+        e2e_err = float(np.linalg.norm((hx2_np - hx_np).ravel()) / np.linalg.norm(hx_np.ravel()))
+        e2e = {"value": nvox / t_e2e / 1e6, "unit": "Mvoxels/s",
+               "h2d_bytes_per_step": (1 + nb) * nvox * esize, "d2h_bytes_per_step": (1 + nb) * nvox * esize,
+               "ms_per_step": t_e2e * 1e3, "pr_rel_err": e2e_err,
+               "api": "nd_dwt_ND(...,'compute','mex').dec/rec -> nddwt_dec_host/nddwt_rec_host, pinned host arrays"}
+        del hx, hy, hx2
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_reference_pair(sizes, wname, level, dtype, len(os.sched_getaffinity(0)))
+
+    line = {
+        "metric": "dec+rec Mvoxels/s", "value": value, "unit": "Mvoxels/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": {"complex64": "c64", "complex128": "c128"}[dtype], "data": "synthetic",
+        "config": {"workload": wl_name, "sizes": list(sizes), "wavelet": wname, "levels": level, "bands": nb,
+                   "elem": dtype, "l2": "working set %.2f GB >> 126 MB L2, no flush" % ((1 + nb) * nvox * esize / 1e9),
+                   "pr_rel_err": pr_err, "dec_ms": dec_ms, "rec_ms": rec_ms, "wall_ms_per_step": t_wall / args.steps * 1e3,
+                   "step_ms_min_med_max": [min(ms), float(np.median(ms)), max(ms)]},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

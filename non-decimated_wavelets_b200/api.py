@@ -176,38 +176,47 @@ class _NdDwtBase:
         return int(level)
 
     # -- dec: nd_dwt_2D.m:141-197 ---------------------------------------------------------
-    def dec(self, x, level):
+    def dec(self, x, level, out=None):
+        """y = obj.dec(x, level).  `out` (optional, host path): a preallocated column-major array
+        of shape [sizes, nb] to write into (e.g. pinned memory reused across an iterative loop)."""
         level = self._check_level(level)
         if torch is not None and isinstance(x, torch.Tensor) and x.is_cuda:
             return self._dec_device(x, level)
         if self.compute.lower() == "gpu" and not (torch is not None and isinstance(x, torch.Tensor)):
             x = to_device(np.asarray(x))
             return self._dec_device(x, level)
-        return self._dec_host(np.asarray(x), level)
+        return self._dec_host(np.asarray(x), level, out)
 
-    def rec(self, y):
+    def rec(self, y, out=None):
         if torch is not None and isinstance(y, torch.Tensor) and y.is_cuda:
             return self._rec_device(y)
         if self.compute.lower() == "gpu" and not (torch is not None and isinstance(y, torch.Tensor)):
             return self._rec_device(to_device(np.asarray(y)))
-        return self._rec_host(np.asarray(y))
+        return self._rec_host(np.asarray(y), out)
 
     def _check_x_shape(self, shape):
         if tuple(shape) != self.sizes:
             raise ValueError("FIlter size and image size not consistant")
 
-    def _dec_host(self, x, level):
+    @staticmethod
+    def _check_out(out, shape, npdt):
+        if out.shape != tuple(shape) or out.dtype != npdt or not out.flags.f_contiguous:
+            raise ValueError("out must be a column-major array of shape %s and dtype %s" % (tuple(shape), npdt))
+        return out
+
+    def _dec_host(self, x, level, out=None):
         if self._ndims == 1 and x.ndim == 2 and 1 in x.shape:
             x = x.reshape(-1)
         self._check_x_shape(x.shape)
         is_c = np.iscomplexobj(x)
         code, npdt = _np_dtype_code(self.precision, is_c)
         xf = np.asfortranarray(x, dtype=npdt)
-        y = np.empty(self.sizes + (self._num_bands(level),), dtype=npdt, order="F")
+        shape = self.sizes + (self._num_bands(level),)
+        y = np.empty(shape, dtype=npdt, order="F") if out is None else self._check_out(out, shape, np.dtype(npdt))
         self._plan(is_c, 0).dec_host(xf.ctypes.data, y.ctypes.data, level)
         return y
 
-    def _rec_host(self, y):
+    def _rec_host(self, y, out=None):
         if y.ndim != self._ndims + 1:
             raise ValueError("FIlter size and image size not consistant")
         self._check_x_shape(y.shape[:-1])
@@ -215,7 +224,7 @@ class _NdDwtBase:
         is_c = np.iscomplexobj(y)
         code, npdt = _np_dtype_code(self.precision, is_c)
         yf = np.asfortranarray(y, dtype=npdt)
-        x = np.empty(self.sizes, dtype=npdt, order="F")
+        x = np.empty(self.sizes, dtype=npdt, order="F") if out is None else self._check_out(out, self.sizes, np.dtype(npdt))
         self._plan(is_c, 0).rec_host(yf.ctypes.data, x.ctypes.data, level)
         return x
 

@@ -1,6 +1,806 @@
-// nddwt_fused.cu -- fused per-level kernels (placeholder until the first fused kernels land).
+// nddwt_fused.cu -- fused per-level kernels for sm_100a: one launch reads the approximation band
+// once and writes all 2^d subbands once (analysis), or reads the 2^d subbands once and writes the
+// reconstructed band once (synthesis).  Direct separable circular lo/hi filtering; no FFT, no
+// stored Fourier-domain filters, no tensor cores (short-filter stencil).
+//
+// Replaces, per level: nd_dwt_dec_1level / nd_dwt_rec_1level (mex/nddwt.c:98-186) and
+// level_1_dec / level_1_rec of Functions/nd_dwt_3D.m:345-393 (and siblings).
+//
+// Analysis kernel (3-D tile pipeline, also the back end of the 4-D path):
+//   * a CTA owns a T1 x T2 column of the (dim1, dim2) plane and marches along dim 3;
+//   * stage A  (dim 3): each thread keeps an L-deep ring of input planes in REGISTERS for its
+//     (T1+L-1) x (T2+L-1) haloed positions, loads one new plane per step straight from global
+//     memory (coalesced along dim 1, periodic wrap folded into precomputed offsets) and emits the
+//     lo3 / hi3 planes into shared memory;
+//   * stage B  (dim 1): 16-byte shared-memory chunks, each thread produces 2*VEC consecutive
+//     outputs for lo1 / hi1 (an XOR chunk swizzle keeps the quarter-warp accesses conflict-free);
+//   * stage C  (dim 2): lanes run along dim 1, each thread slides a register window down R2 rows
+//     and streams the 8 subbands to global memory with fully coalesced st.global.cs.
+//   complex-single arithmetic is FFMA2 (fma.rn.f32x2) on (re, im) pairs with duplicated taps
+//   taken from the kernel-parameter constant bank.
+#include <cstdlib>
 #include "nddwt_plan.h"
+
 namespace nddwt {
-int fused_dec_level(nddwt_plan *, int, const void *, const LevelIO &, void *const *, cudaStream_t) { return 1; }
-int fused_rec_level(nddwt_plan *, int, const void *const *, void *, cudaStream_t) { return 1; }
+
+// ---------------------------------------------------------------------------------------------
+// tap storage in kernel parameters: complex single keeps each tap duplicated (t, t) so that one
+// FFMA2 updates (re, im) at once.
+template <typename T> struct TapOf { using type = typename Elem<T>::R; };
+template <> struct TapOf<float2> { using type = float2; };
+
+__device__ __forceinline__ void macp(float &acc, float g, float v) { acc = fmaf(g, v, acc); }
+__device__ __forceinline__ void macp(double &acc, double g, double v) { acc = fma(g, v, acc); }
+__device__ __forceinline__ void macp(float2 &acc, float2 g, float2 v) { acc = __ffma2_rn(g, v, acc); }
+__device__ __forceinline__ void macp(double2 &acc, double g, double2 v)
+{
+    acc.x = fma(g, v.x, acc.x);
+    acc.y = fma(g, v.y, acc.y);
 }
+
+static inline float mk_tap(float, double v) { return (float)v; }
+static inline double mk_tap(double, double v) { return v; }
+static inline float2 mk_tap(float2, double v) { return make_float2((float)v, (float)v); }
+
+template <typename T, int L>
+struct FusedTaps {
+    typename TapOf<T>::type lo[3][L];
+    typename TapOf<T>::type hi[3][L];
+};
+
+template <typename T>
+struct Dec3Params {
+    const T *in[2];     // 3-D: in[0] = local planes [n3][n2][n1]; 4-D back end: lo4 / hi4 arrays
+    const T *halo_lo;   // planes below the slab (ascending), or nullptr   (3-D slabs only)
+    const T *halo_hi;   // planes above the slab, or nullptr
+    T *out[16];         // subband bases (8 per input array)
+    int n1, n2, n3;
+    int64_t s3;         // plane stride (elements)
+    int64_t s4;         // hyperplane stride (4-D batches)
+    int nhyp;           // hyperplanes per input array (1 for 3-D)
+    int tiles1, tiles2, zc, nchunks;
+    int halo_below;     // planes held by halo_lo
+};
+
+__device__ __forceinline__ int wrapi(int m, int n)
+{
+    m %= n;
+    return m < 0 ? m + n : m;
+}
+
+__device__ __forceinline__ int swz(int chunk) { return chunk ^ ((chunk >> 3) & 1); }
+
+template <typename T> __device__ __forceinline__ T ldg_stream(const T *p) { return __ldg(p); }
+
+template <typename T> __device__ __forceinline__ void st_stream(T *p, T v) { __stcs(p, v); }
+
+template <typename T, int VEC>
+__device__ __forceinline__ void ld_chunk(const T *p, T *dst)
+{
+    const uint4 q = *reinterpret_cast<const uint4 *>(p);
+    union { uint4 u; T t[VEC]; } cv;
+    cv.u = q;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) dst[i] = cv.t[i];
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void st_chunk(T *p, const T *src)
+{
+    union { uint4 u; T t[VEC]; } cv;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) cv.t[i] = src[i];
+    *reinterpret_cast<uint4 *>(p) = cv.u;
+}
+
+// ---- compile-time geometry ---------------------------------------------------------------
+template <typename T, int L, int T2>
+struct Geo {
+    static constexpr int VEC = 16 / (int)sizeof(T);   // elements per 16-byte chunk
+    static constexpr int R1 = 2 * VEC;                // dim-1 outputs per stage-B item (two chunks)
+    static constexpr int T1 = 8 * R1;                 // tile width = 16 chunks
+    static constexpr int H = L - 1, HB = L / 2 - 1, HA = L / 2;
+    static constexpr int W1 = T1 + H, W2 = T2 + H;
+    static constexpr int W2P = (W2 + 7) & ~7;         // rows padded to whole quarter-warps (stage B lanes run along rows)
+    static constexpr int PAC = ((W1 + VEC - 1) / VEC) | 1;   // SA row pitch in chunks, odd -> conflict-free column access
+    static constexpr int PA = PAC * VEC;
+    static constexpr int PBC = 17;                    // SB row pitch in chunks (16 + 1 pad, odd)
+    static constexpr int PB = PBC * VEC;
+    static constexpr int NPOS = W1 * W2;
+    static constexpr int NCH = (R1 + L - 1 + VEC - 1) / VEC;   // chunks read per stage-B item
+    static constexpr size_t SMEM = (size_t)(2 * W2 * PA + 4 * W2 * PB) * sizeof(T);
+};
+
+// ---- stage A for ring phase U (all ring indices static -> the ring stays in registers) ----
+template <typename T, int L, int PPT, int U>
+__device__ __forceinline__ void dec_stage_a(T (&ring)[PPT][L], const typename TapOf<T>::type *lo,
+                                            const typename TapOf<T>::type *hi, T *sa_lo, T *sa_hi,
+                                            const int (&sa_off)[PPT], const int (&g_off)[PPT], int npos_mask,
+                                            const T *next_plane)
+{
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        T alo = zero_of(T()), ahi = zero_of(T());
+#pragma unroll
+        for (int j = 0; j < L; ++j) {
+            const T v = ring[k][(U + j) % L];
+            macp(alo, lo[L - 1 - j], v);
+            macp(ahi, hi[L - 1 - j], v);
+        }
+        if (npos_mask & (1 << k)) {
+            sa_lo[sa_off[k]] = alo;
+            sa_hi[sa_off[k]] = ahi;
+        }
+    }
+    if (next_plane != nullptr) {
+#pragma unroll
+        for (int k = 0; k < PPT; ++k)
+            if (npos_mask & (1 << k)) ring[k][U] = ldg_stream(next_plane + g_off[k]);
+    }
+}
+
+template <typename T, int L, int PPT, int U>
+struct DispatchA {
+    __device__ __forceinline__ static void run(int u, T (&ring)[PPT][L], const typename TapOf<T>::type *lo,
+                                               const typename TapOf<T>::type *hi, T *sa_lo, T *sa_hi,
+                                               const int (&sa_off)[PPT], const int (&g_off)[PPT], int mask,
+                                               const T *next_plane)
+    {
+        if (u == U) dec_stage_a<T, L, PPT, U>(ring, lo, hi, sa_lo, sa_hi, sa_off, g_off, mask, next_plane);
+        else DispatchA<T, L, PPT, U + 1>::run(u, ring, lo, hi, sa_lo, sa_hi, sa_off, g_off, mask, next_plane);
+    }
+};
+template <typename T, int L, int PPT>
+struct DispatchA<T, L, PPT, L> {
+    __device__ __forceinline__ static void run(int, T (&)[PPT][L], const typename TapOf<T>::type *,
+                                               const typename TapOf<T>::type *, T *, T *, const int (&)[PPT],
+                                               const int (&)[PPT], int, const T *) {}
+};
+
+template <typename T, int L, int T2, int NT, int R2, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
+{
+    using G = Geo<T, L, T2>;
+    constexpr int VEC = G::VEC, R1 = G::R1, T1 = G::T1, HB = G::HB, HA = G::HA;
+    constexpr int W1 = G::W1, W2 = G::W2, W2P = G::W2P, PA = G::PA, PB = G::PB, NPOS = G::NPOS, NCH = G::NCH;
+    constexpr int PPT = (NPOS + NT - 1) / NT;
+    constexpr int NRUN = T2 / R2;
+    constexpr int NB_ITEMS = 2 * 8 * W2P, KB = (NB_ITEMS + NT - 1) / NT;
+    constexpr int NC_ITEMS = 4 * NRUN * 16, KC = (NC_ITEMS + NT - 1) / NT;
+    static_assert(T2 % R2 == 0, "R2 must divide T2");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *SA = reinterpret_cast<T *>(smem_raw);     // [2][W2][PA]   lo3 / hi3 of the haloed tile
+    T *SB = SA + 2 * W2 * PA;                    // [4][W2][PB]   (b1 + 2 b3), rows still haloed
+
+    const int tid = threadIdx.x;
+    int bid = blockIdx.x;
+    const int t1 = bid % p.tiles1;
+    bid /= p.tiles1;
+    const int t2 = bid % p.tiles2;
+    bid /= p.tiles2;
+    const int chunk = bid % p.nchunks;
+    const int batch = bid / p.nchunks;
+    const int a1 = t1 * T1, a2 = t2 * T2;
+    const int z0 = chunk * p.zc;
+    const int z1 = min(z0 + p.zc, p.n3);
+    const int n1 = p.n1, n2 = p.n2, n3 = p.n3;
+    const int64_t s3 = p.s3;
+    const bool slab = (p.halo_lo != nullptr) || (p.halo_hi != nullptr);
+    // batch (4-D back end): input array `bsel` at hyperplane `bhyp`; output bands 8*bsel.. at the same hyperplane
+    const int bsel = batch / p.nhyp, bhyp = batch - bsel * p.nhyp;
+    const T *in_base = p.in[bsel] + (int64_t)bhyp * p.s4;
+    const int64_t out_boff = (int64_t)bhyp * p.s4;
+
+    auto plane_ptr = [&](int zi) -> const T * {
+        if (!slab) return in_base + (int64_t)wrapi(zi, n3) * s3;
+        if (zi < 0) return p.halo_lo + (int64_t)(zi + p.halo_below) * s3;
+        if (zi >= n3) return p.halo_hi + (int64_t)(zi - n3) * s3;
+        return in_base + (int64_t)zi * s3;
+    };
+
+    // ---- per-thread constants, hoisted out of the marching loop -------------------------
+    // stage A: haloed positions (global in-plane offset with the periodic wrap folded in, SA slot)
+    int g_off[PPT], sa_off[PPT];
+    int mask = 0;
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        const int q = tid + k * NT;
+        const int r = q / W1, c = q - r * W1;
+        if (q < NPOS) mask |= 1 << k;
+        g_off[k] = wrapi(a2 - HB + r, n2) * n1 + wrapi(a1 - HB + c, n1);
+        sa_off[k] = r * PA + c;
+    }
+    // stage B: item = (array a, chunk pair cb, row r), lanes run along rows
+    int b_src[KB], b_dst[KB];
+    int b_mask = 0;
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+        const int it = tid + k * NT;
+        const int r = it % W2P, g = it / W2P;
+        const int cb = g & 7, a = g >> 3;
+        if (it < NB_ITEMS && r < W2) b_mask |= 1 << k;
+        b_src[k] = (a * W2 + r) * PA + cb * R1;
+        b_dst[k] = (2 * a * W2 + r) * PB + cb * R1;
+    }
+    // stage C: item = (array m, run, chunk column cp); lanes run along dim 1
+    int c_src[KC];
+    T *c_lo[KC], *c_hi[KC];
+    int c_rows[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        const int it = tid + k * NT;
+        const int cp = it & 15, rest = it >> 4;
+        const int run = rest % NRUN, m = rest / NRUN;
+        c_src[k] = (m * W2 + run * R2) * PB + cp * VEC;
+        const int g1 = a1 + cp * VEC, g2 = a2 + run * R2;
+        int rows = min(R2, n2 - g2);
+        if (it >= NC_ITEMS || g1 >= n1 || rows < 0) rows = 0;
+        c_rows[k] = rows;
+        const int mm = (it < NC_ITEMS) ? m : 0;
+        const int64_t off = out_boff + (int64_t)z0 * s3 + (int64_t)g2 * n1 + g1;
+        c_lo[k] = p.out[8 * bsel + (mm & 1) + 4 * (mm >> 1)] + off;
+        c_hi[k] = p.out[8 * bsel + (mm & 1) + 4 * (mm >> 1) + 2] + off;
+    }
+
+    // warm-up: planes z0-HB .. z0+HA fill ring slots 0..L-1
+    T ring[PPT][L];
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+        const T *pl = plane_ptr(z0 - HB + j);
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) ring[k][j] = (mask & (1 << k)) ? ldg_stream(pl + g_off[k]) : zero_of(T());
+    }
+
+    T *sa_lo = SA, *sa_hi = SA + W2 * PA;
+    int u = 0;
+    for (int z = z0; z < z1; ++z) {
+        const T *next_plane = (z + 1 < z1) ? plane_ptr(z + 1 + HA) : nullptr;
+        DispatchA<T, L, PPT, 0>::run(u, ring, tp.lo[2], tp.hi[2], sa_lo, sa_hi, sa_off, g_off, mask, next_plane);
+        u = (u + 1 == L) ? 0 : u + 1;
+        __syncthreads();
+
+        // ---- stage B: dim 1, SA[a][r][:] -> SB[b1 + 2a][r][:]
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            if (b_mask & (1 << k)) {
+                const T *row = SA + b_src[k];
+                T v[NCH * VEC];
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) ld_chunk<T, VEC>(row + j * VEC, v + j * VEC);
+                T *d0 = SB + b_dst[k];
+                T acc[R1];
+#pragma unroll
+                for (int o = 0; o < R1; ++o) {
+                    acc[o] = zero_of(T());
+#pragma unroll
+                    for (int j = 0; j < L; ++j) macp(acc[o], tp.lo[0][L - 1 - j], v[o + j]);
+                }
+                st_chunk<T, VEC>(d0, acc);
+                st_chunk<T, VEC>(d0 + VEC, acc + VEC);
+#pragma unroll
+                for (int o = 0; o < R1; ++o) {
+                    acc[o] = zero_of(T());
+#pragma unroll
+                    for (int j = 0; j < L; ++j) macp(acc[o], tp.hi[0][L - 1 - j], v[o + j]);
+                }
+                st_chunk<T, VEC>(d0 + W2 * PB, acc);
+                st_chunk<T, VEC>(d0 + W2 * PB + VEC, acc + VEC);
+            }
+        }
+        __syncthreads();
+
+        // ---- stage C: dim 2, SB[m][rows][chunk] -> subbands in global memory (16-byte streaming stores)
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            const int rows = c_rows[k];
+            if (rows > 0) {
+                const T *col = SB + c_src[k];
+                T v[R2 + L - 1][VEC];
+#pragma unroll
+                for (int j = 0; j < R2 + L - 1; ++j) ld_chunk<T, VEC>(col + j * PB, v[j]);
+#pragma unroll
+                for (int o = 0; o < R2; ++o) {
+                    T lo[VEC], hi[VEC];
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        lo[e] = zero_of(T());
+                        hi[e] = zero_of(T());
+#pragma unroll
+                        for (int j = 0; j < L; ++j) {
+                            macp(lo[e], tp.lo[1][L - 1 - j], v[o + j][e]);
+                            macp(hi[e], tp.hi[1][L - 1 - j], v[o + j][e]);
+                        }
+                    }
+                    if (o < rows) {
+                        union { uint4 q; T t[VEC]; } a, b;
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) { a.t[e] = lo[e]; b.t[e] = hi[e]; }
+                        __stcs(reinterpret_cast<uint4 *>(c_lo[k] + (int64_t)o * n1), a.q);
+                        __stcs(reinterpret_cast<uint4 *>(c_hi[k] + (int64_t)o * n1), b.q);
+                    }
+                }
+            }
+            c_lo[k] += s3;
+            c_hi[k] += s3;
+        }
+        // SA is rewritten by the next stage A only after the barrier that follows stage B of this
+        // step; SB is rewritten after the barrier that follows the next stage A: no third barrier.
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Synthesis kernel (3-D, also the back end of the 4-D path): reads the 8 subbands once, writes the
+// reconstructed band once; the band sum and the 2^-d normalisation (folded into the taps) are fused.
+//   stage RA (dim 2): straight from global memory -- lanes run along dim 1 (coalesced), each thread
+//            slides a register window down R2 rows for the (b2 = 0, b2 = 1) pair of one (b1, b3) group;
+//   stage RB (dim 1): 16-byte shared-memory chunks, lanes run along rows (odd chunk pitch);
+//   stage RC (dim 3): scatter form -- each thread owns one 16-byte output chunk and an L-deep ring of
+//            partial sums in registers; a plane is stored (st.global.cs) when its last tap has arrived.
+template <typename T>
+struct Rec3Params {
+    const T *in[16];    // subbands (8 per output array)
+    T *out[2];          // 3-D: out[0]; 4-D back end: u_lo / u_hi
+    int n1, n2, n3;
+    int64_t s3, s4;
+    int nhyp;
+    int tiles1, tiles2, zc, nchunks;
+};
+
+template <typename T, int L, int T2>
+struct GeoR {
+    static constexpr int VEC = 16 / (int)sizeof(T);
+    static constexpr int R1 = 2 * VEC;
+    static constexpr int T1 = 8 * R1;
+    static constexpr int H = L - 1, HB = L / 2, HA = L / 2 - 1;   // synthesis reads n-L/2 .. n+L/2-1
+    static constexpr int W1 = T1 + H, W2 = T2 + H;
+    static constexpr int PUC = ((W1 + VEC - 1) / VEC) | 1;
+    static constexpr int PU = PUC * VEC;          // U pitch (elements), odd chunk count
+    static constexpr int PV = 17 * VEC;           // V pitch
+    static constexpr int NCH = (R1 + L - 1 + VEC - 1) / VEC;
+    static constexpr size_t SMEM = (size_t)(4 * T2 * PU + 2 * T2 * PV) * sizeof(T);
+};
+
+template <typename T, int L, int VEC, int U>
+__device__ __forceinline__ void rec_stage_c(T (&acc)[L][VEC], const T (&v0)[VEC], const T (&v1)[VEC],
+                                            const typename TapOf<T>::type *lo, const typename TapOf<T>::type *hi,
+                                            T *dst, bool store)
+{
+    // coefficient plane t (phase U = t mod L) feeds output planes n = z0 + t - k, slot (U - k) mod L
+#pragma unroll
+    for (int k = 0; k < L; ++k) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            macp(acc[(U - k + L) % L][e], lo[k], v0[e]);
+            macp(acc[(U - k + L) % L][e], hi[k], v1[e]);
+        }
+    }
+    // plane n = z0 + t - (L-1) is complete: slot (U + 1) mod L
+    if (store) {
+        union { uint4 q; T t[VEC]; } a;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) a.t[e] = acc[(U + 1) % L][e];
+        __stcs(reinterpret_cast<uint4 *>(dst), a.q);
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[(U + 1) % L][e] = zero_of(T());
+}
+
+template <typename T, int L, int VEC, int U>
+struct DispatchC {
+    __device__ __forceinline__ static void run(int u, T (&acc)[L][VEC], const T (&v0)[VEC], const T (&v1)[VEC],
+                                               const typename TapOf<T>::type *lo, const typename TapOf<T>::type *hi,
+                                               T *dst, bool store)
+    {
+        if (u == U) rec_stage_c<T, L, VEC, U>(acc, v0, v1, lo, hi, dst, store);
+        else DispatchC<T, L, VEC, U + 1>::run(u, acc, v0, v1, lo, hi, dst, store);
+    }
+};
+template <typename T, int L, int VEC>
+struct DispatchC<T, L, VEC, L> {
+    __device__ __forceinline__ static void run(int, T (&)[L][VEC], const T (&)[VEC], const T (&)[VEC],
+                                               const typename TapOf<T>::type *, const typename TapOf<T>::type *, T *,
+                                               bool) {}
+};
+
+template <typename T, int L, int T2, int NT, int R2, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_rec3_fused(const Rec3Params<T> p, const FusedTaps<T, L> tp)
+{
+    using G = GeoR<T, L, T2>;
+    constexpr int VEC = G::VEC, R1 = G::R1, T1 = G::T1, HB = G::HB, H = G::H;
+    constexpr int W1 = G::W1, PU = G::PU, PV = G::PV, NCH = G::NCH;
+    constexpr int NRUN = T2 / R2;
+    constexpr int NA_ITEMS = 4 * NRUN * W1, KA = (NA_ITEMS + NT - 1) / NT;
+    constexpr int NB_ITEMS = 2 * 8 * T2, KB = (NB_ITEMS + NT - 1) / NT;
+    constexpr int NC_ITEMS = T2 * 16, KC = (NC_ITEMS + NT - 1) / NT;
+    static_assert(T2 % R2 == 0 && T2 % 8 == 0, "tile rows");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *SU = reinterpret_cast<T *>(smem_raw);     // [4][T2][PU]  (b1 + 2 b3), dim 2 synthesised
+    T *SV = SU + 4 * T2 * PU;                    // [2][T2][PV]  (b3), dims 1,2 synthesised
+
+    const int tid = threadIdx.x;
+    int bid = blockIdx.x;
+    const int t1 = bid % p.tiles1;
+    bid /= p.tiles1;
+    const int t2 = bid % p.tiles2;
+    bid /= p.tiles2;
+    const int chunk = bid % p.nchunks;
+    const int batch = bid / p.nchunks;
+    const int a1 = t1 * T1, a2 = t2 * T2;
+    const int z0 = chunk * p.zc;
+    const int z1 = min(z0 + p.zc, p.n3);
+    const int n1 = p.n1, n2 = p.n2, n3 = p.n3;
+    const int64_t s3 = p.s3;
+    const int bsel = batch / p.nhyp, bhyp = batch - bsel * p.nhyp;
+    const int64_t boff = (int64_t)bhyp * p.s4;
+    const bool rows_interior = (a2 - HB >= 0) && (a2 - HB + T2 + H <= n2);
+
+    // ---- hoisted per-thread constants ----
+    // stage RA: item = (q = b1 + 2 b3, run, haloed column c)
+    const T *a_lo[KA], *a_hi[KA];
+    int a_dst[KA], a_row0[KA];
+    int a_mask = 0;
+#pragma unroll
+    for (int k = 0; k < KA; ++k) {
+        const int it = tid + k * NT;
+        const int c = it % W1, g = it / W1;
+        const int run = g % NRUN, q = (it < NA_ITEMS) ? g / NRUN : 0;
+        if (it < NA_ITEMS) a_mask |= 1 << k;
+        const int blo = 8 * bsel + (q & 1) + 4 * (q >> 1);
+        const int gcol = wrapi(a1 - HB + c, n1);
+        a_row0[k] = a2 - HB + run * R2;                 // first (unwrapped) global row of the window
+        a_lo[k] = p.in[blo] + boff + gcol;
+        a_hi[k] = p.in[blo + 2] + boff + gcol;
+        a_dst[k] = (q * T2 + run * R2) * PU + c;
+    }
+    // stage RB: item = (b3, chunk pair cb, row j), lanes run along rows
+    int b_src[KB], b_dst[KB];
+    int b_mask = 0;
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+        const int it = tid + k * NT;
+        const int j = it % T2, g = it / T2;
+        const int cb = g & 7, b3 = (g >> 3) & 1;
+        if (it < NB_ITEMS) b_mask |= 1 << k;
+        b_src[k] = (2 * b3 * T2 + j) * PU + cb * R1;
+        b_dst[k] = (b3 * T2 + j) * PV + cb * R1;
+    }
+    // stage RC: item = output chunk (row j, chunk column cp)
+    int c_src[KC];
+    T *c_out[KC];
+    bool c_ok[KC];
+    T acc[KC][L][VEC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        const int it = tid + k * NT;
+        const int cp = it & 15, j = it >> 4;
+        c_src[k] = j * PV + cp * VEC;
+        const int g1 = a1 + cp * VEC, g2 = a2 + j;
+        c_ok[k] = (it < NC_ITEMS) && g1 < n1 && g2 < n2;
+        // pointer to output plane (z0 - (L-1)): advanced by s3 per step, first stored at step t = L-1
+        c_out[k] = p.out[bsel] + boff + ((int64_t)z0 - (L - 1)) * s3 + (int64_t)g2 * n1 + g1;
+#pragma unroll
+        for (int s = 0; s < L; ++s)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[k][s][e] = zero_of(T());
+    }
+
+    const int nsteps = (z1 - z0) + L - 1;
+    int u = 0;
+    for (int t = 0; t < nsteps; ++t) {
+        const int zc = wrapi(z0 - HB + t, n3);
+        const int64_t zoff = (int64_t)zc * s3;
+
+        // ---- stage RA: dim 2 from global memory
+#pragma unroll
+        for (int k = 0; k < KA; ++k) {
+            if (a_mask & (1 << k)) {
+                T o[R2];
+#pragma unroll
+                for (int i = 0; i < R2; ++i) o[i] = zero_of(T());
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    const T *src = (hb ? a_hi[k] : a_lo[k]) + zoff;
+                    const typename TapOf<T>::type *g = hb ? tp.hi[1] : tp.lo[1];
+                    T w[R2 + L - 1];
+                    if (rows_interior) {
+#pragma unroll
+                        for (int i = 0; i < R2 + L - 1; ++i) w[i] = ldg_stream(src + (int64_t)(a_row0[k] + i) * n1);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < R2 + L - 1; ++i) w[i] = ldg_stream(src + (int64_t)wrapi(a_row0[k] + i, n2) * n1);
+                    }
+#pragma unroll
+                    for (int i = 0; i < R2; ++i)
+#pragma unroll
+                        for (int kk = 0; kk < L; ++kk) macp(o[i], g[kk], w[i + kk]);
+                }
+                T *dst = SU + a_dst[k];
+#pragma unroll
+                for (int i = 0; i < R2; ++i) dst[i * PU] = o[i];
+            }
+        }
+        __syncthreads();
+
+        // ---- stage RB: dim 1, SU[b1 + 2 b3][j][:] -> SV[b3][j][:]
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            if (b_mask & (1 << k)) {
+                T o[R1];
+#pragma unroll
+                for (int i = 0; i < R1; ++i) o[i] = zero_of(T());
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    const T *row = SU + b_src[k] + hb * T2 * PU;
+                    const typename TapOf<T>::type *g = hb ? tp.hi[0] : tp.lo[0];
+                    T v[NCH * VEC];
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j) ld_chunk<T, VEC>(row + j * VEC, v + j * VEC);
+#pragma unroll
+                    for (int i = 0; i < R1; ++i)
+#pragma unroll
+                        for (int kk = 0; kk < L; ++kk) macp(o[i], g[kk], v[i + kk]);
+                }
+                st_chunk<T, VEC>(SV + b_dst[k], o);
+                st_chunk<T, VEC>(SV + b_dst[k] + VEC, o + VEC);
+            }
+        }
+        __syncthreads();
+
+        // ---- stage RC: dim 3, scatter into the register ring of partial sums
+        const bool store = (t >= L - 1);
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            if (tid + k * NT < NC_ITEMS) {
+                T v0[VEC], v1[VEC];
+                ld_chunk<T, VEC>(SV + c_src[k], v0);
+                ld_chunk<T, VEC>(SV + c_src[k] + T2 * PV, v1);
+                DispatchC<T, L, VEC, 0>::run(u, acc[k], v0, v1, tp.lo[2], tp.hi[2], c_out[k], store && c_ok[k]);
+                c_out[k] += s3;
+            }
+        }
+        u = (u + 1 == L) ? 0 : u + 1;
+        // SU is rewritten by the next stage RA only after both barriers of this step; SV after the
+        // barrier that follows the next stage RA.
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <typename T, int L>
+static FusedTaps<T, L> make_taps(const nddwt_plan *p, bool rec)
+{
+    FusedTaps<T, L> t;
+    const AllTaps<double> &src = rec ? p->rec_d : p->dec_d;
+    for (int d = 0; d < 3; ++d)
+        for (int k = 0; k < L; ++k) {
+            const int dd = d < p->ndims ? d : 0;
+            t.lo[d][k] = mk_tap(typename TapOf<T>::type(), src.d[dd].lo[k]);
+            t.hi[d][k] = mk_tap(typename TapOf<T>::type(), src.d[dd].hi[k]);
+        }
+    return t;
+}
+
+static int pick_zc(int n3, int tiles, int H, int ctas_per_wave)
+{
+    // choose planes per chunk: enough CTAs to fill the machine several times, while keeping the
+    // ring warm-up (L planes re-read per chunk) a small fraction of the chunk
+    int best = n3;
+    double best_cost = 1e30;
+    for (int zc = 4; zc <= n3; ++zc) {
+        const int nch = (n3 + zc - 1) / zc;
+        const double ctas = (double)tiles * nch;
+        const double waves = ctas / ctas_per_wave;
+        const double eff = waves / (double)((int64_t)(waves + 0.999999));   // tail efficiency
+        const double work = (double)(zc + 0.35 * (H + 1)) / zc;              // warm-up overhead (loads only)
+        const double cost = work / eff;
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = zc; }
+    }
+    if (n3 < 4) best = n3;
+    return best;
+}
+
+template <typename T, int L, int T2, int NT, int R2, int MINB>
+static int launch_dec3_v(nddwt_plan *p, const Dec3Params<T> &base, cudaStream_t s)
+{
+    using G = Geo<T, L, T2>;
+    Dec3Params<T> prm = base;
+    prm.tiles1 = (prm.n1 + G::T1 - 1) / G::T1;
+    prm.tiles2 = (prm.n2 + T2 - 1) / T2;
+    const int batches = prm.nhyp * (prm.in[1] ? 2 : 1);
+    prm.zc = pick_zc(prm.n3, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB);
+    prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
+    prm.halo_below = (L / 2 - 1);
+    auto kern = k_dec3_fused<T, L, T2, NT, R2, MINB>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        attr_done = true;
+    }
+    const FusedTaps<T, L> tp = make_taps<T, L>(p, false);
+    const int64_t grid = (int64_t)prm.tiles1 * prm.tiles2 * prm.nchunks * batches;
+    kern<<<(unsigned)grid, NT, G::SMEM, s>>>(prm, tp);
+    p->launches++;
+    NDDWT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int tuning_variant()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("NDDWT_VARIANT");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+template <typename T, int L>
+static int launch_dec3(nddwt_plan *p, const void *a_in, const LevelIO &io, void *const *out_bands, cudaStream_t s)
+{
+    Dec3Params<T> prm;
+    prm.in[0] = reinterpret_cast<const T *>(a_in);
+    prm.in[1] = nullptr;
+    prm.s4 = 0;
+    prm.nhyp = 1;
+    prm.halo_lo = reinterpret_cast<const T *>(io.halo_lo);
+    prm.halo_hi = reinterpret_cast<const T *>(io.halo_hi);
+    for (int b = 0; b < 8; ++b) prm.out[b] = reinterpret_cast<T *>(out_bands[b]);
+    for (int b = 8; b < 16; ++b) prm.out[b] = nullptr;
+    prm.n1 = (int)p->dims[0];
+    prm.n2 = (int)p->dims[1];
+    prm.n3 = (int)p->dims[2];
+    prm.s3 = p->dims[0] * p->dims[1];
+    if constexpr (L == 8 && sizeof(T) == 8 && Elem<T>::cplx) {   // tuning variants (env NDDWT_VARIANT) for the headline case
+        switch (tuning_variant() % 10) {
+            case 1: return launch_dec3_v<T, L, 16, 256, 4, 2>(p, prm, s);
+            case 2: return launch_dec3_v<T, L, 32, 512, 4, 1>(p, prm, s);
+            case 3: return launch_dec3_v<T, L, 16, 256, 4, 1>(p, prm, s);
+            case 4: return launch_dec3_v<T, L, 8, 256, 4, 2>(p, prm, s);
+            case 5: return launch_dec3_v<T, L, 16, 384, 4, 1>(p, prm, s);
+            default: break;
+        }
+    }
+    return launch_dec3_v<T, L, 16, 256, 2, 2>(p, prm, s);
+}
+
+template <typename T>
+static int dispatch_dec3(nddwt_plan *p, int L, const void *a_in, const LevelIO &io, void *const *out_bands,
+                         cudaStream_t s)
+{
+    switch (L) {
+        case 2: return launch_dec3<T, 2>(p, a_in, io, out_bands, s);
+        case 4: return launch_dec3<T, 4>(p, a_in, io, out_bands, s);
+        case 6: return launch_dec3<T, 6>(p, a_in, io, out_bands, s);
+        case 8: return launch_dec3<T, 8>(p, a_in, io, out_bands, s);
+        default: return 1;
+    }
+}
+
+
+static int pick_zc_rec(int n3, int units_per_plane_chunk, int H, int slots)
+{
+    // synthesis pays the full pipeline for the L-1 warm-up planes of every chunk: minimise
+    // ceil(units / slots) * (zc + H)
+    int best = n3;
+    double best_cost = 1e30;
+    for (int nch = 1; nch <= n3; ++nch) {
+        const int zc = (n3 + nch - 1) / nch;
+        if (zc < 4 && nch > 1) break;
+        const int64_t units = (int64_t)units_per_plane_chunk * ((n3 + zc - 1) / zc);
+        const double cost = (double)((units + slots - 1) / slots) * (zc + H);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = zc; }
+    }
+    return best;
+}
+
+template <typename T, int L, int T2, int NT, int R2, int MINB>
+static int launch_rec3_v(nddwt_plan *p, const Rec3Params<T> &base, cudaStream_t s)
+{
+    using G = GeoR<T, L, T2>;
+    Rec3Params<T> prm = base;
+    prm.tiles1 = (prm.n1 + G::T1 - 1) / G::T1;
+    prm.tiles2 = (prm.n2 + T2 - 1) / T2;
+    const int batches = prm.nhyp * (prm.out[1] ? 2 : 1);
+    prm.zc = pick_zc_rec(prm.n3, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB);
+    prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
+    auto kern = k_rec3_fused<T, L, T2, NT, R2, MINB>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        attr_done = true;
+    }
+    const FusedTaps<T, L> tp = make_taps<T, L>(p, true);
+    const int64_t grid = (int64_t)prm.tiles1 * prm.tiles2 * prm.nchunks * batches;
+    kern<<<(unsigned)grid, NT, G::SMEM, s>>>(prm, tp);
+    p->launches++;
+    NDDWT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, int L>
+static int launch_rec3(nddwt_plan *p, const void *const *in_bands, void *a_out, cudaStream_t s)
+{
+    Rec3Params<T> prm;
+    for (int b = 0; b < 8; ++b) prm.in[b] = reinterpret_cast<const T *>(in_bands[b]);
+    for (int b = 8; b < 16; ++b) prm.in[b] = nullptr;
+    prm.out[0] = reinterpret_cast<T *>(a_out);
+    prm.out[1] = nullptr;
+    prm.n1 = (int)p->dims[0];
+    prm.n2 = (int)p->dims[1];
+    prm.n3 = (int)p->dims[2];
+    prm.s3 = p->dims[0] * p->dims[1];
+    prm.s4 = 0;
+    prm.nhyp = 1;
+    if constexpr (L == 8 && sizeof(T) == 8 && Elem<T>::cplx) {
+        switch (tuning_variant() / 10) {
+            case 1: return launch_rec3_v<T, L, 16, 256, 8, 2>(p, prm, s);
+            case 2: return launch_rec3_v<T, L, 16, 320, 4, 2>(p, prm, s);
+            case 3: return launch_rec3_v<T, L, 16, 256, 4, 2>(p, prm, s);
+            case 4: return launch_rec3_v<T, L, 16, 320, 8, 1>(p, prm, s);
+            default: break;
+        }
+    }
+    return launch_rec3_v<T, L, 16, 320, 8, 2>(p, prm, s);
+}
+
+template <typename T>
+static int dispatch_rec3(nddwt_plan *p, int L, const void *const *in_bands, void *a_out, cudaStream_t s)
+{
+    switch (L) {
+        case 2: return launch_rec3<T, 2>(p, in_bands, a_out, s);
+        case 4: return launch_rec3<T, 4>(p, in_bands, a_out, s);
+        case 6: return launch_rec3<T, 6>(p, in_bands, a_out, s);
+        case 8: return launch_rec3<T, 8>(p, in_bands, a_out, s);
+        default: return 1;
+    }
+}
+
+static bool uniform_taps(const nddwt_plan *p)
+{
+    for (int i = 1; i < p->ndims; ++i)
+        if (p->L[i] != p->L[0]) return false;
+    return true;
+}
+
+int fused_dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io, void *const *out_bands,
+                    cudaStream_t s)
+{
+    if (dil != 1 || !uniform_taps(p)) return 1;
+    if (p->ndims == 3) {
+        if (p->dims[0] * p->dims[1] >= (int64_t)1 << 30) return 1;
+        if (p->dims[0] < p->L[0] || p->dims[1] < p->L[1]) return 1;
+        if (p->dims[0] % (16 / (int64_t)p->esize) != 0) return 1;   // 16-byte row alignment for the vector stores
+        switch (p->dtype) {
+            case NDDWT_C64: return dispatch_dec3<float2>(p, p->L[0], a_in, io, out_bands, s);
+            case NDDWT_F32: return dispatch_dec3<float>(p, p->L[0], a_in, io, out_bands, s);
+            case NDDWT_F64: return dispatch_dec3<double>(p, p->L[0], a_in, io, out_bands, s);
+            case NDDWT_C128: return dispatch_dec3<double2>(p, p->L[0], a_in, io, out_bands, s);
+        }
+    }
+    return 1;
+}
+
+int fused_rec_level(nddwt_plan *p, int dil, const void *const *in_bands, void *a_out, cudaStream_t s)
+{
+    if (dil != 1 || !uniform_taps(p)) return 1;
+    if (p->ndims == 3) {
+        if (p->dims[0] * p->dims[1] >= (int64_t)1 << 30) return 1;
+        if (p->dims[0] < p->L[0] || p->dims[1] < p->L[1]) return 1;
+        if (p->dims[0] % (16 / (int64_t)p->esize) != 0) return 1;
+        switch (p->dtype) {
+            case NDDWT_C64: return dispatch_rec3<float2>(p, p->L[0], in_bands, a_out, s);
+            case NDDWT_F32: return dispatch_rec3<float>(p, p->L[0], in_bands, a_out, s);
+            case NDDWT_F64: return dispatch_rec3<double>(p, p->L[0], in_bands, a_out, s);
+            case NDDWT_C128: return dispatch_rec3<double2>(p, p->L[0], in_bands, a_out, s);
+        }
+    }
+    return 1;
+}
+
+}  // namespace nddwt
