@@ -384,6 +384,10 @@ int nddwt_rec_level_slab_stage1(nddwt_plan *p, int level_index, const void *cons
     if (rc) return rc;
     if (!in_bands || !u_lo || !u_hi) { set_error("null pointer"); return NDDWT_ERR_ARG; }
     NDDWT_CUDA(cudaSetDevice(p->device));
+    if (p->kernel_mode == 0) {
+        rc = fused_rec_stage1(p, p->dil[level_index - 1], in_bands, u_lo, u_hi, reinterpret_cast<cudaStream_t>(stream));
+        if (rc <= 0) { p->last_path = 1; return rc; }
+    }
     p->last_path = 0;
     return generic_rec_stage1(p, p->dil[level_index - 1], in_bands, u_lo, u_hi,
                               reinterpret_cast<cudaStream_t>(stream));
@@ -399,6 +403,11 @@ int nddwt_rec_level_slab_stage2(nddwt_plan *p, int level_index, const void *u_lo
     LevelIO io;
     io.halo_lo = halo_lo;
     io.halo_hi = halo_hi;
+    if (p->kernel_mode == 0) {
+        rc = fused_rec_stage2(p, p->dil[level_index - 1], u_lo, u_hi, io, a_out, reinterpret_cast<cudaStream_t>(stream));
+        if (rc <= 0) { p->last_path = 1; return rc; }
+    }
+    p->last_path = 0;
     return generic_rec_stage2(p, p->dil[level_index - 1], u_lo, u_hi, io, a_out,
                               reinterpret_cast<cudaStream_t>(stream));
 }

@@ -170,7 +170,7 @@ k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
     constexpr int NC_ITEMS = 4 * NRUN * 16, KC = (NC_ITEMS + NT - 1) / NT;
     static_assert(T2 % R2 == 0, "R2 must divide T2");
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     T *SA = reinterpret_cast<T *>(smem_raw);     // [2][W2][PA]   lo3 / hi3 of the haloed tile
     T *SB = SA + 2 * W2 * PA;                    // [4][W2][PB]   (b1 + 2 b3), rows still haloed
 
@@ -347,6 +347,7 @@ struct Rec3Params {
     int64_t s3, s4;
     int nhyp;
     int tiles1, tiles2, zc, nchunks;
+    int prefetch;       // 0 none, 1 prefetch.global.L1 of the next plane's footprint, 2 prefetch.global.L2
 };
 
 template <typename T, int L, int T2>
@@ -418,7 +419,7 @@ k_rec3_fused(const Rec3Params<T> p, const FusedTaps<T, L> tp)
     constexpr int NC_ITEMS = T2 * 16, KC = (NC_ITEMS + NT - 1) / NT;
     static_assert(T2 % R2 == 0 && T2 % 8 == 0, "tile rows");
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     T *SU = reinterpret_cast<T *>(smem_raw);     // [4][T2][PU]  (b1 + 2 b3), dim 2 synthesised
     T *SV = SU + 4 * T2 * PU;                    // [2][T2][PV]  (b3), dims 1,2 synthesised
 
@@ -489,11 +490,36 @@ k_rec3_fused(const Rec3Params<T> p, const FusedTaps<T, L> tp)
             for (int e = 0; e < VEC; ++e) acc[k][s][e] = zero_of(T());
     }
 
+    // next-plane prefetch: one 128-byte line per (band, haloed row, segment), spread over the threads
+    constexpr int SEG = (W1 * (int)sizeof(T) + 127) / 128 + 1;
+    constexpr int NPF = 8 * (T2 + H) * SEG, KP = (NPF + NT - 1) / NT;
+    const T *pf_ptr[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        const int it = tid + k * NT;
+        const int sg = it % SEG, g = it / SEG;
+        const int r = g % (T2 + H), b = (it < NPF) ? g / (T2 + H) : 0;
+        const int col = wrapi(a1 - HB + sg * (128 / (int)sizeof(T)), n1);
+        pf_ptr[k] = (it < NPF && sg * (128 / (int)sizeof(T)) < W1 + (128 / (int)sizeof(T)))
+                        ? p.in[8 * bsel + b] + boff + (int64_t)wrapi(a2 - HB + r, n2) * n1 + col
+                        : nullptr;
+    }
+
     const int nsteps = (z1 - z0) + L - 1;
     int u = 0;
     for (int t = 0; t < nsteps; ++t) {
         const int zc = wrapi(z0 - HB + t, n3);
         const int64_t zoff = (int64_t)zc * s3;
+        if (p.prefetch && t + 1 < nsteps) {
+            const int64_t znext = (int64_t)wrapi(z0 - HB + t + 1, n3) * s3;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                if (pf_ptr[k] != nullptr) {
+                    if (p.prefetch == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf_ptr[k] + znext));
+                    else asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_ptr[k] + znext));
+                }
+            }
+        }
 
         // ---- stage RA: dim 2 from global memory
 #pragma unroll
@@ -566,6 +592,374 @@ k_rec3_fused(const Rec3Params<T> p, const FusedTaps<T, L> tp)
         u = (u + 1 == L) ? 0 : u + 1;
         // SU is rewritten by the next stage RA only after both barriers of this step; SV after the
         // barrier that follows the next stage RA.
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Synthesis kernel, bulk-copy (TMA engine) staged variant.  The haloed tiles of the 8 subbands of
+// the NEXT coefficient plane are brought into shared memory by cp.async.bulk (UBLKCP) row copies
+// that complete on an mbarrier, while stages RB / RC of the current plane run.  The periodic
+// boundary costs nothing: a row that crosses the array edge is issued as two copies.  Stage RA then
+// slides its window over shared memory with immediate offsets (no address arithmetic, no exposed
+// global-load latency).
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <typename T, int L, int T2>
+struct GeoRB {
+    static constexpr int VEC = 16 / (int)sizeof(T);
+    static constexpr int R1 = 2 * VEC;
+    static constexpr int T1 = 8 * R1;
+    static constexpr int H = L - 1, HB = L / 2, HA = L / 2 - 1;
+    static constexpr int HBAL = (HB + VEC - 1) / VEC * VEC;              // staged rows start 16-byte aligned
+    static constexpr int SHIFT = HBAL - HB;                              // column of the first needed element
+    static constexpr int W1S = (HBAL + T1 + HA + VEC - 1) / VEC * VEC;   // staged row width (elements)
+    static constexpr int W1 = T1 + H, W2 = T2 + H;
+    static constexpr int PUC = ((W1 + VEC - 1) / VEC) | 1;
+    static constexpr int PU = PUC * VEC;
+    static constexpr int PV = 17 * VEC;
+    static constexpr int NCH = (R1 + L - 1 + VEC - 1) / VEC;
+    static constexpr size_t RAW_ELEMS = (size_t)8 * W2 * W1S;
+    static constexpr size_t SMEM = (RAW_ELEMS + 4 * T2 * PU + 2 * T2 * PV) * sizeof(T) + 16;
+};
+
+template <typename T, int L, int T2, int NT, int R2, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp)
+{
+    using G = GeoRB<T, L, T2>;
+    constexpr int VEC = G::VEC, R1 = G::R1, T1 = G::T1, HB = G::HB, HBAL = G::HBAL, SHIFT = G::SHIFT;
+    constexpr int W1 = G::W1, W2 = G::W2, W1S = G::W1S, PU = G::PU, PV = G::PV, NCH = G::NCH;
+    constexpr int NRUN = T2 / R2;
+    constexpr int NA_ITEMS = 4 * NRUN * W1, KA = (NA_ITEMS + NT - 1) / NT;
+    constexpr int NB_ITEMS = 2 * 8 * T2, KB = (NB_ITEMS + NT - 1) / NT;
+    constexpr int NC_ITEMS = T2 * 16, KC = (NC_ITEMS + NT - 1) / NT;
+    constexpr int NROWS = 8 * W2, KR = (NROWS + NT - 1) / NT;       // staged rows per plane
+    constexpr uint32_t PLANE_BYTES = (uint32_t)(G::RAW_ELEMS * sizeof(T));
+    static_assert(T2 % R2 == 0 && T2 % 8 == 0, "tile rows");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T *RAW = reinterpret_cast<T *>(smem_raw);          // [8][W2][W1S]  haloed subband tiles of one plane
+    T *SU = RAW + G::RAW_ELEMS;                         // [4][T2][PU]
+    T *SV = SU + 4 * T2 * PU;                           // [2][T2][PV]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(SV + 2 * T2 * PV);
+
+    const int tid = threadIdx.x;
+    int bid = blockIdx.x;
+    const int t1 = bid % p.tiles1;
+    bid /= p.tiles1;
+    const int t2 = bid % p.tiles2;
+    bid /= p.tiles2;
+    const int chunk = bid % p.nchunks;
+    const int batch = bid / p.nchunks;
+    const int a1 = t1 * T1, a2 = t2 * T2;
+    const int z0 = chunk * p.zc;
+    const int z1 = min(z0 + p.zc, p.n3);
+    const int n1 = p.n1, n2 = p.n2, n3 = p.n3;
+    const int64_t s3 = p.s3;
+    const int bsel = batch / p.nhyp, bhyp = batch - bsel * p.nhyp;
+    const int64_t boff = (int64_t)bhyp * p.s4;
+
+    // ---- hoisted per-thread constants ----
+    // row copies: (band b, haloed row r) -> up to two contiguous segments (periodic wrap along dim 1)
+    const T *r_src[KR];
+    int r_dst[KR], r_len0[KR];          // first segment length (elements); the second one is W1S - len0
+    int r_col1[KR];                     // global column where the second segment starts
+#pragma unroll
+    for (int k = 0; k < KR; ++k) {
+        const int it = tid + k * NT;
+        const int r = it % W2, b = (it < NROWS) ? it / W2 : 0;
+        const int grow = wrapi(a2 - HB + r, n2);
+        const int gc0 = wrapi(a1 - HBAL, n1);
+        r_src[k] = p.in[8 * bsel + b] + boff + (int64_t)grow * n1;
+        r_dst[k] = (it < NROWS) ? (b * W2 + r) * W1S : -1;
+        r_len0[k] = min(W1S, n1 - gc0);
+        r_col1[k] = gc0;                // segment 0 starts at gc0, segment 1 (if any) at column 0
+    }
+    // stage RA: item = (q = b1 + 2 b3, run, haloed column c)
+    int a_src[KA], a_dst[KA];
+    int a_mask = 0;
+#pragma unroll
+    for (int k = 0; k < KA; ++k) {
+        const int it = tid + k * NT;
+        const int c = it % W1, g = it / W1;
+        const int run = g % NRUN, q = (it < NA_ITEMS) ? g / NRUN : 0;
+        if (it < NA_ITEMS) a_mask |= 1 << k;
+        const int blo = (q & 1) + 4 * (q >> 1);
+        a_src[k] = (blo * W2 + run * R2) * W1S + SHIFT + c;
+        a_dst[k] = (q * T2 + run * R2) * PU + c;
+    }
+    int b_src[KB], b_dst[KB];
+    int b_mask = 0;
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+        const int it = tid + k * NT;
+        const int j = it % T2, g = it / T2;
+        const int cb = g & 7, b3 = (g >> 3) & 1;
+        if (it < NB_ITEMS) b_mask |= 1 << k;
+        b_src[k] = (2 * b3 * T2 + j) * PU + cb * R1;
+        b_dst[k] = (b3 * T2 + j) * PV + cb * R1;
+    }
+    int c_src[KC];
+    T *c_out[KC];
+    bool c_ok[KC];
+    T acc[KC][L][VEC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        const int it = tid + k * NT;
+        const int cp = it & 15, j = it >> 4;
+        c_src[k] = j * PV + cp * VEC;
+        const int g1 = a1 + cp * VEC, g2 = a2 + j;
+        c_ok[k] = (it < NC_ITEMS) && g1 < n1 && g2 < n2;
+        c_out[k] = p.out[bsel] + boff + ((int64_t)z0 - (L - 1)) * s3 + (int64_t)g2 * n1 + g1;
+#pragma unroll
+        for (int s = 0; s < L; ++s)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[k][s][e] = zero_of(T());
+    }
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // the expect_tx of thread 0 must precede every complete_tx of the same phase: warp 0 issues it
+    // first inside issue_plane; the other warps' copies may only start after it -> barrier
+    const int nsteps = (z1 - z0) + L - 1;
+    if (tid < 32) { if (tid == 0) mbar_expect_tx(bar, PLANE_BYTES); }
+    __syncthreads();
+    {
+        const int64_t zoff = (int64_t)wrapi(z0 - HB, n3) * s3;
+#pragma unroll
+        for (int k = 0; k < KR; ++k) {
+            if (r_dst[k] >= 0) {
+                const T *src = r_src[k] + zoff;
+                T *dst = RAW + r_dst[k];
+                const int len0 = r_len0[k];
+                bulk_g2s(dst, src + r_col1[k], (uint32_t)(len0 * sizeof(T)), bar);
+                if (len0 < W1S) bulk_g2s(dst + len0, src, (uint32_t)((W1S - len0) * sizeof(T)), bar);
+            }
+        }
+    }
+
+    int u = 0;
+    uint32_t parity = 0;
+    for (int t = 0; t < nsteps; ++t) {
+        mbar_wait(bar, parity);
+        parity ^= 1;
+
+        // ---- stage RA: dim 2 out of the staged tiles
+#pragma unroll
+        for (int k = 0; k < KA; ++k) {
+            if (a_mask & (1 << k)) {
+                T o[R2];
+#pragma unroll
+                for (int i = 0; i < R2; ++i) o[i] = zero_of(T());
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    const T *src = RAW + a_src[k] + hb * 2 * W2 * W1S;
+                    const typename TapOf<T>::type *g = hb ? tp.hi[1] : tp.lo[1];
+                    T w[R2 + L - 1];
+#pragma unroll
+                    for (int i = 0; i < R2 + L - 1; ++i) w[i] = src[i * W1S];
+#pragma unroll
+                    for (int i = 0; i < R2; ++i)
+#pragma unroll
+                        for (int kk = 0; kk < L; ++kk) macp(o[i], g[kk], w[i + kk]);
+                }
+                T *dst = SU + a_dst[k];
+#pragma unroll
+                for (int i = 0; i < R2; ++i) dst[i * PU] = o[i];
+            }
+        }
+        __syncthreads();   // RAW fully consumed, SU complete
+
+        // ---- stage the next coefficient plane while RB / RC run
+        if (t + 1 < nsteps) {
+            if (tid == 0) mbar_expect_tx(bar, PLANE_BYTES);
+            const int64_t zoff = (int64_t)wrapi(z0 - HB + t + 1, n3) * s3;
+#pragma unroll
+            for (int k = 0; k < KR; ++k) {
+                if (r_dst[k] >= 0) {
+                    const T *src = r_src[k] + zoff;
+                    T *dst = RAW + r_dst[k];
+                    const int len0 = r_len0[k];
+                    bulk_g2s(dst, src + r_col1[k], (uint32_t)(len0 * sizeof(T)), bar);
+                    if (len0 < W1S) bulk_g2s(dst + len0, src, (uint32_t)((W1S - len0) * sizeof(T)), bar);
+                }
+            }
+        }
+
+        // ---- stage RB: dim 1
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            if (b_mask & (1 << k)) {
+                T o[R1];
+#pragma unroll
+                for (int i = 0; i < R1; ++i) o[i] = zero_of(T());
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    const T *row = SU + b_src[k] + hb * T2 * PU;
+                    const typename TapOf<T>::type *g = hb ? tp.hi[0] : tp.lo[0];
+                    T v[NCH * VEC];
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j) ld_chunk<T, VEC>(row + j * VEC, v + j * VEC);
+#pragma unroll
+                    for (int i = 0; i < R1; ++i)
+#pragma unroll
+                        for (int kk = 0; kk < L; ++kk) macp(o[i], g[kk], v[i + kk]);
+                }
+                st_chunk<T, VEC>(SV + b_dst[k], o);
+                st_chunk<T, VEC>(SV + b_dst[k] + VEC, o + VEC);
+            }
+        }
+        __syncthreads();
+
+        // ---- stage RC: dim 3 scatter ring
+        const bool store = (t >= L - 1);
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            if (tid + k * NT < NC_ITEMS) {
+                T v0[VEC], v1[VEC];
+                ld_chunk<T, VEC>(SV + c_src[k], v0);
+                ld_chunk<T, VEC>(SV + c_src[k] + T2 * PV, v1);
+                DispatchC<T, L, VEC, 0>::run(u, acc[k], v0, v1, tp.lo[2], tp.hi[2], c_out[k], store && c_ok[k]);
+                c_out[k] += s3;
+            }
+        }
+        u = (u + 1 == L) ? 0 : u + 1;
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Last-dimension passes of the 4-D path (and the slab-exchange points of the multi-GPU path):
+// one thread owns one 16-byte chunk of the (dim 1..3) hyperplane and marches along dim 4 with an
+// L-deep register ring, so every input hyperplane is read exactly once.
+template <typename T, int L>
+struct LastTaps {
+    typename TapOf<T>::type lo[L];
+    typename TapOf<T>::type hi[L];
+};
+
+template <typename T, int L>
+__global__ void __launch_bounds__(256)
+k_dec_last(const T *__restrict__ in, const T *__restrict__ halo_lo, const T *__restrict__ halo_hi,
+           T *__restrict__ out_lo, T *__restrict__ out_hi, int64_t nchunks, int n4, int64_t s4, int below,
+           const LastTaps<T, L> tp)
+{
+    constexpr int VEC = 16 / (int)sizeof(T), HB = L / 2 - 1, HA = L / 2;
+    const int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= nchunks) return;
+    const bool slab = (halo_lo != nullptr) || (halo_hi != nullptr);
+    auto plane_ptr = [&](int zi) -> const T * {
+        if (!slab) return in + (int64_t)wrapi(zi, n4) * s4;
+        if (zi < 0) return halo_lo + (int64_t)(zi + below) * s4;
+        if (zi >= n4) return halo_hi + (int64_t)(zi - n4) * s4;
+        return in + (int64_t)zi * s4;
+    };
+    const int64_t off = ci * VEC;
+    T ring[L][VEC];
+#pragma unroll
+    for (int j = 0; j < L; ++j) ld_chunk<T, VEC>(plane_ptr(j - HB) + off, ring[j]);
+    for (int zb = 0; zb < n4; zb += L) {
+#pragma unroll
+        for (int u = 0; u < L; ++u) {
+            const int z = zb + u;
+            if (z < n4) {
+                T lo[VEC], hi[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    lo[e] = zero_of(T());
+                    hi[e] = zero_of(T());
+#pragma unroll
+                    for (int j = 0; j < L; ++j) {
+                        macp(lo[e], tp.lo[L - 1 - j], ring[(u + j) % L][e]);
+                        macp(hi[e], tp.hi[L - 1 - j], ring[(u + j) % L][e]);
+                    }
+                }
+                if (z + 1 < n4) ld_chunk<T, VEC>(plane_ptr(z + 1 + HA) + off, ring[u]);
+                st_chunk<T, VEC>(out_lo + (int64_t)z * s4 + off, lo);
+                st_chunk<T, VEC>(out_hi + (int64_t)z * s4 + off, hi);
+            }
+        }
+    }
+}
+
+template <typename T, int L>
+__global__ void __launch_bounds__(256)
+k_rec_last(const T *__restrict__ u_lo, const T *__restrict__ u_hi, const T *__restrict__ halo_lo,
+           const T *__restrict__ halo_hi, T *__restrict__ out, int64_t nchunks, int n4, int64_t s4, int below,
+           int above, const LastTaps<T, L> tp)
+{
+    constexpr int VEC = 16 / (int)sizeof(T), HB = L / 2;
+    const int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= nchunks) return;
+    const bool slab = (halo_lo != nullptr) || (halo_hi != nullptr);
+    const int64_t off = ci * VEC;
+    T acc[L][VEC];
+#pragma unroll
+    for (int j = 0; j < L; ++j)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[j][e] = zero_of(T());
+    const int nsteps = n4 + L - 1;
+    for (int tb = 0; tb < nsteps; tb += L) {
+#pragma unroll
+        for (int u = 0; u < L; ++u) {
+            const int t = tb + u;
+            if (t < nsteps) {
+                const int zi = t - HB;          // coefficient hyperplane (may lie in the halo)
+                const T *pl, *ph;
+                if (!slab) {
+                    const int64_t o = (int64_t)wrapi(zi, n4) * s4;
+                    pl = u_lo + o;
+                    ph = u_hi + o;
+                } else if (zi < 0) {
+                    pl = halo_lo + (int64_t)(zi + below) * s4;
+                    ph = halo_lo + (int64_t)(zi + 2 * below) * s4;
+                } else if (zi >= n4) {
+                    pl = halo_hi + (int64_t)(zi - n4) * s4;
+                    ph = halo_hi + (int64_t)(zi - n4 + above) * s4;
+                } else {
+                    pl = u_lo + (int64_t)zi * s4;
+                    ph = u_hi + (int64_t)zi * s4;
+                }
+                T v0[VEC], v1[VEC];
+                ld_chunk<T, VEC>(pl + off, v0);
+                ld_chunk<T, VEC>(ph + off, v1);
+                // output hyperplane n = t - (L-1) completes at this step
+                DispatchC<T, L, VEC, 0>::run(u, acc, v0, v1, tp.lo, tp.hi, out + (int64_t)(t - (L - 1)) * s4 + off,
+                                             t >= L - 1);
+            }
+        }
     }
 }
 
@@ -709,7 +1103,37 @@ static int launch_rec3_v(nddwt_plan *p, const Rec3Params<T> &base, cudaStream_t 
     const int batches = prm.nhyp * (prm.out[1] ? 2 : 1);
     prm.zc = pick_zc_rec(prm.n3, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB);
     prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
+    {
+        static int pf = -1;
+        if (pf < 0) { const char *e = getenv("NDDWT_PREFETCH"); pf = e ? atoi(e) : 0; }
+        prm.prefetch = pf;
+    }
     auto kern = k_rec3_fused<T, L, T2, NT, R2, MINB>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        attr_done = true;
+    }
+    const FusedTaps<T, L> tp = make_taps<T, L>(p, true);
+    const int64_t grid = (int64_t)prm.tiles1 * prm.tiles2 * prm.nchunks * batches;
+    kern<<<(unsigned)grid, NT, G::SMEM, s>>>(prm, tp);
+    p->launches++;
+    NDDWT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, int L, int T2, int NT, int R2, int MINB>
+static int launch_rec3_bulk(nddwt_plan *p, const Rec3Params<T> &base, cudaStream_t s)
+{
+    using G = GeoRB<T, L, T2>;
+    Rec3Params<T> prm = base;
+    prm.tiles1 = (prm.n1 + G::T1 - 1) / G::T1;
+    prm.tiles2 = (prm.n2 + T2 - 1) / T2;
+    const int batches = prm.nhyp * (prm.out[1] ? 2 : 1);
+    prm.zc = pick_zc_rec(prm.n3, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB);
+    prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
+    prm.prefetch = 0;
+    auto kern = k_rec3_bulk<T, L, T2, NT, R2, MINB>;
     static bool attr_done = false;
     if (!attr_done) {
         NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
@@ -743,9 +1167,13 @@ static int launch_rec3(nddwt_plan *p, const void *const *in_bands, void *a_out, 
             case 2: return launch_rec3_v<T, L, 16, 320, 4, 2>(p, prm, s);
             case 3: return launch_rec3_v<T, L, 16, 256, 4, 2>(p, prm, s);
             case 4: return launch_rec3_v<T, L, 16, 320, 8, 1>(p, prm, s);
+            case 5: if (prm.n1 >= GeoRB<T, L, 16>::W1S) return launch_rec3_bulk<T, L, 16, 320, 8, 2>(p, prm, s); break;
+            case 6: if (prm.n1 >= GeoRB<T, L, 16>::W1S) return launch_rec3_bulk<T, L, 16, 256, 8, 2>(p, prm, s); break;
+            case 7: if (prm.n1 >= GeoRB<T, L, 16>::W1S) return launch_rec3_bulk<T, L, 16, 320, 4, 2>(p, prm, s); break;
             default: break;
         }
     }
+    if (prm.n1 >= GeoRB<T, L, 16>::W1S) return launch_rec3_bulk<T, L, 16, 320, 8, 2>(p, prm, s);
     return launch_rec3_v<T, L, 16, 320, 8, 2>(p, prm, s);
 }
 
@@ -768,6 +1196,188 @@ static bool uniform_taps(const nddwt_plan *p)
     return true;
 }
 
+
+static bool uniform_taps(const nddwt_plan *p);
+// ------------------------------- 4-D path ---------------------------------------------------
+template <typename T, int L>
+static LastTaps<T, L> make_last_taps(const nddwt_plan *p, bool rec)
+{
+    LastTaps<T, L> t;
+    const AllTaps<double> &src = rec ? p->rec_d : p->dec_d;
+    const int d = p->ndims - 1;
+    for (int k = 0; k < L; ++k) {
+        t.lo[k] = mk_tap(typename TapOf<T>::type(), src.d[d].lo[k]);
+        t.hi[k] = mk_tap(typename TapOf<T>::type(), src.d[d].hi[k]);
+    }
+    return t;
+}
+
+static int ensure_fused_scratch(nddwt_plan *p, size_t bytes)
+{
+    if (p->fused_scratch_bytes < bytes) {
+        if (p->fused_scratch) { cudaFree(p->fused_scratch); p->fused_scratch = nullptr; p->fused_scratch_bytes = 0; }
+        NDDWT_CUDA(cudaMalloc(&p->fused_scratch, bytes));
+        p->fused_scratch_bytes = bytes;
+    }
+    return 0;
+}
+
+template <typename T, int L>
+static int launch_dec_last(nddwt_plan *p, const T *in, const LevelIO &io, T *out_lo, T *out_hi, cudaStream_t s)
+{
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const int d = p->ndims - 1;
+    int64_t s4 = 1;
+    for (int i = 0; i < d; ++i) s4 *= p->dims[i];
+    const int64_t nchunks = s4 / VEC;
+    const int n4 = (int)p->dims[d];
+    const unsigned grid = (unsigned)((nchunks + 255) / 256);
+    k_dec_last<T, L><<<grid, 256, 0, s>>>(in, reinterpret_cast<const T *>(io.halo_lo),
+                                         reinterpret_cast<const T *>(io.halo_hi), out_lo, out_hi, nchunks, n4, s4,
+                                         L / 2 - 1, make_last_taps<T, L>(p, false));
+    p->launches++;
+    NDDWT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, int L>
+static int launch_rec_last(nddwt_plan *p, const T *u_lo, const T *u_hi, const LevelIO &io, T *out, cudaStream_t s)
+{
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const int d = p->ndims - 1;
+    int64_t s4 = 1;
+    for (int i = 0; i < d; ++i) s4 *= p->dims[i];
+    const int64_t nchunks = s4 / VEC;
+    const int n4 = (int)p->dims[d];
+    const unsigned grid = (unsigned)((nchunks + 255) / 256);
+    k_rec_last<T, L><<<grid, 256, 0, s>>>(u_lo, u_hi, reinterpret_cast<const T *>(io.halo_lo),
+                                         reinterpret_cast<const T *>(io.halo_hi), out, nchunks, n4, s4, L / 2,
+                                         L / 2 - 1, make_last_taps<T, L>(p, true));
+    p->launches++;
+    NDDWT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, int L>
+static int dec4_level(nddwt_plan *p, const void *a_in, const LevelIO &io, void *const *out_bands, cudaStream_t s)
+{
+    const size_t band_bytes = (size_t)p->numel * p->esize;
+    int rc = ensure_fused_scratch(p, 2 * band_bytes);
+    if (rc) return rc;
+    T *lo4 = reinterpret_cast<T *>(p->fused_scratch);
+    T *hi4 = lo4 + p->numel;
+    rc = launch_dec_last<T, L>(p, reinterpret_cast<const T *>(a_in), io, lo4, hi4, s);
+    if (rc) return rc;
+    Dec3Params<T> prm;
+    prm.in[0] = lo4;
+    prm.in[1] = hi4;
+    prm.halo_lo = nullptr;
+    prm.halo_hi = nullptr;
+    for (int b = 0; b < 16; ++b) prm.out[b] = reinterpret_cast<T *>(out_bands[b]);
+    prm.n1 = (int)p->dims[0];
+    prm.n2 = (int)p->dims[1];
+    prm.n3 = (int)p->dims[2];
+    prm.s3 = p->dims[0] * p->dims[1];
+    prm.s4 = prm.s3 * p->dims[2];
+    prm.nhyp = (int)p->dims[3];
+    return launch_dec3_v<T, L, 16, 256, 2, 2>(p, prm, s);
+}
+
+template <typename T, int L>
+static int rec4_stage1(nddwt_plan *p, const void *const *in_bands, T *u_lo, T *u_hi, cudaStream_t s)
+{
+    Rec3Params<T> prm;
+    for (int b = 0; b < 16; ++b) prm.in[b] = reinterpret_cast<const T *>(in_bands[b]);
+    prm.out[0] = u_lo;
+    prm.out[1] = u_hi;
+    prm.n1 = (int)p->dims[0];
+    prm.n2 = (int)p->dims[1];
+    prm.n3 = (int)p->dims[2];
+    prm.s3 = p->dims[0] * p->dims[1];
+    prm.s4 = prm.s3 * p->dims[2];
+    prm.nhyp = (int)p->dims[3];
+    if (prm.n1 >= GeoRB<T, L, 16>::W1S) return launch_rec3_bulk<T, L, 16, 320, 8, 2>(p, prm, s);
+    return launch_rec3_v<T, L, 16, 320, 8, 2>(p, prm, s);
+}
+
+template <typename T, int L>
+static int rec4_level(nddwt_plan *p, const void *const *in_bands, void *a_out, cudaStream_t s)
+{
+    const size_t band_bytes = (size_t)p->numel * p->esize;
+    int rc = ensure_fused_scratch(p, 2 * band_bytes);
+    if (rc) return rc;
+    T *u_lo = reinterpret_cast<T *>(p->fused_scratch);
+    T *u_hi = u_lo + p->numel;
+    rc = rec4_stage1<T, L>(p, in_bands, u_lo, u_hi, s);
+    if (rc) return rc;
+    LevelIO none;
+    return launch_rec_last<T, L>(p, u_lo, u_hi, none, reinterpret_cast<T *>(a_out), s);
+}
+
+#define NDDWT_L_SWITCH(L_, CALL)                \
+    switch (L_) {                               \
+        case 2: { constexpr int LL = 2; return CALL; } \
+        case 4: { constexpr int LL = 4; return CALL; } \
+        case 6: { constexpr int LL = 6; return CALL; } \
+        case 8: { constexpr int LL = 8; return CALL; } \
+        default: return 1;                      \
+    }
+
+template <typename T>
+static int dispatch_dec4(nddwt_plan *p, const void *a_in, const LevelIO &io, void *const *out_bands, cudaStream_t s)
+{
+    NDDWT_L_SWITCH(p->L[0], (dec4_level<T, LL>(p, a_in, io, out_bands, s)));
+}
+template <typename T>
+static int dispatch_rec4(nddwt_plan *p, const void *const *in_bands, void *a_out, cudaStream_t s)
+{
+    NDDWT_L_SWITCH(p->L[0], (rec4_level<T, LL>(p, in_bands, a_out, s)));
+}
+template <typename T>
+static int dispatch_rec4_stage1(nddwt_plan *p, const void *const *in_bands, void *u_lo, void *u_hi, cudaStream_t s)
+{
+    NDDWT_L_SWITCH(p->L[0], (rec4_stage1<T, LL>(p, in_bands, reinterpret_cast<T *>(u_lo), reinterpret_cast<T *>(u_hi), s)));
+}
+template <typename T>
+static int dispatch_rec_last(nddwt_plan *p, const void *u_lo, const void *u_hi, const LevelIO &io, void *a_out,
+                             cudaStream_t s)
+{
+    NDDWT_L_SWITCH(p->L[p->ndims - 1], (launch_rec_last<T, LL>(p, reinterpret_cast<const T *>(u_lo),
+                                                                 reinterpret_cast<const T *>(u_hi), io,
+                                                                 reinterpret_cast<T *>(a_out), s)));
+}
+
+static bool fused_geometry_ok(const nddwt_plan *p)
+{
+    if (p->ndims < 3) return false;
+    if (p->dims[0] * p->dims[1] >= (int64_t)1 << 30) return false;
+    if (p->dims[0] < p->L[0] || p->dims[1] < p->L[1]) return false;
+    if (p->dims[0] % (16 / (int64_t)p->esize) != 0) return false;   // 16-byte rows (vector stores, bulk copies)
+    return true;
+}
+
+#define NDDWT_T_SWITCH(p_, CALL)                                   \
+    switch ((p_)->dtype) {                                         \
+        case NDDWT_C64: { using TT = float2; return CALL; }        \
+        case NDDWT_F32: { using TT = float; return CALL; }         \
+        case NDDWT_F64: { using TT = double; return CALL; }        \
+        case NDDWT_C128: { using TT = double2; return CALL; }      \
+        default: return 1;                                         \
+    }
+
+int fused_rec_stage1(nddwt_plan *p, int dil, const void *const *in_bands, void *u_lo, void *u_hi, cudaStream_t s)
+{
+    if (dil != 1 || !uniform_taps(p) || p->ndims != 4 || !fused_geometry_ok(p)) return 1;
+    NDDWT_T_SWITCH(p, (dispatch_rec4_stage1<TT>(p, in_bands, u_lo, u_hi, s)));
+}
+
+int fused_rec_stage2(nddwt_plan *p, int dil, const void *u_lo, const void *u_hi, const LevelIO &io, void *a_out,
+                     cudaStream_t s)
+{
+    if (dil != 1 || p->ndims != 4 || !fused_geometry_ok(p)) return 1;
+    NDDWT_T_SWITCH(p, (dispatch_rec_last<TT>(p, u_lo, u_hi, io, a_out, s)));
+}
+
 int fused_dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io, void *const *out_bands,
                     cudaStream_t s)
 {
@@ -782,6 +1392,9 @@ int fused_dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io,
             case NDDWT_F64: return dispatch_dec3<double>(p, p->L[0], a_in, io, out_bands, s);
             case NDDWT_C128: return dispatch_dec3<double2>(p, p->L[0], a_in, io, out_bands, s);
         }
+    }
+    if (p->ndims == 4 && fused_geometry_ok(p)) {
+        NDDWT_T_SWITCH(p, (dispatch_dec4<TT>(p, a_in, io, out_bands, s)));
     }
     return 1;
 }
@@ -799,6 +1412,9 @@ int fused_rec_level(nddwt_plan *p, int dil, const void *const *in_bands, void *a
             case NDDWT_F64: return dispatch_rec3<double>(p, p->L[0], in_bands, a_out, s);
             case NDDWT_C128: return dispatch_rec3<double2>(p, p->L[0], in_bands, a_out, s);
         }
+    }
+    if (p->ndims == 4 && fused_geometry_ok(p)) {
+        NDDWT_T_SWITCH(p, (dispatch_rec4<TT>(p, in_bands, a_out, s)));
     }
     return 1;
 }
