@@ -1,0 +1,211 @@
+"""Multi-GPU path: slabs along the LAST dimension, one process per GPU, periodic halo exchange.
+
+The reference has no multi-device code; this module is the B200-native extension
+BASELINE.json's north_star asks for.  Rank r owns a contiguous block of planes of the last
+dimension of x and of every subband.  Per level:
+
+  analysis   needs (L/2 - 1) planes of the approximation band from below and L/2 from above
+             (L = taps along the last dim) -> one grouped send/recv on the periodic ring, then the
+             slab kernel (nddwt_dec_level_slab);
+  synthesis  is split at the slab dimension: stage 1 synthesises dims 1..d-1 locally and sums the
+             band bits into two arrays u_lo / u_hi, their L/2 (below) and L/2 - 1 (above) halo planes
+             are exchanged, stage 2 finishes along the last dim (nddwt_rec_level_slab_stage1/2).
+
+When the halo is wider than a neighbour's slab (cfg4 at 8 GPUs: 4 planes per rank, 7 halo planes)
+planes come from several ranks; `halo_sources` resolves every needed plane to (owner, local index).
+
+`torch.distributed` is only the plumbing (NCCL on GPUs; gloo in the CPU tests); the compute engine
+is the CUDA library.  The engine is pluggable so the host logic can be tested on CPU with a
+numpy stand-in (tests/test_slab_gloo.py) -- the product default has no CPU engine.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+try:
+    import torch
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    torch = None
+    dist = None
+
+
+def slab_partition(n_last, world):
+    """Contiguous, at most +-1 ragged split of n_last planes over `world` ranks -> [(start, count)]."""
+    base, rem = divmod(int(n_last), int(world))
+    out, s = [], 0
+    for r in range(world):
+        c = base + (1 if r < rem else 0)
+        out.append((s, c))
+        s += c
+    return out
+
+
+def owner_of(plane, parts):
+    for r, (s, c) in enumerate(parts):
+        if s <= plane < s + c:
+            return r, plane - s
+    raise ValueError("plane out of range")
+
+
+def halo_sources(n_last, world, rank, below, above):
+    """Global planes a rank needs around its slab, resolved to (owner rank, local index).
+    Returns (lo, hi): lists ordered by ascending global position (periodic)."""
+    parts = slab_partition(n_last, world)
+    s, c = parts[rank]
+    lo = [owner_of((s - below + i) % n_last, parts) for i in range(below)]
+    hi = [owner_of((s + c + i) % n_last, parts) for i in range(above)]
+    return lo, hi
+
+
+def _runs(entries):
+    """Group consecutive (owner, idx) entries into (owner, first_idx, count, dst_offset) runs."""
+    runs, i = [], 0
+    while i < len(entries):
+        o, idx = entries[i]
+        j = i + 1
+        while j < len(entries) and entries[j][0] == o and entries[j][1] == entries[j - 1][1] + 1:
+            j += 1
+        runs.append((o, idx, j - i, i))
+        i = j
+    return runs
+
+
+class HaloExchanger:
+    """Precomputed send/recv schedule for one (below, above) halo shape on the periodic ring."""
+
+    def __init__(self, n_last, world, rank, below, above, group=None):
+        self.n_last, self.world, self.rank, self.below, self.above, self.group = n_last, world, rank, below, above, group
+        self.recv_lo = _runs(halo_sources(n_last, world, rank, below, above)[0])
+        self.recv_hi = _runs(halo_sources(n_last, world, rank, below, above)[1])
+        # what every other rank needs from me
+        self.send = []   # (peer, first_idx, count, tag)
+        for peer in range(world):
+            plo, phi = halo_sources(n_last, world, peer, below, above)
+            for which, runs in ((0, _runs(plo)), (1, _runs(phi))):
+                for k, (o, idx, cnt, _) in enumerate(runs):
+                    if o == rank:
+                        self.send.append((peer, idx, cnt, which, k))
+
+    def exchange(self, local, halo_lo, halo_hi):
+        """local: [n_local, ...] contiguous; halo_lo: [below, ...]; halo_hi: [above, ...] (filled in place).
+        Planes a rank needs from itself are copied locally."""
+        ops, pending_self = [], []
+        for which, runs, dst in ((0, self.recv_lo, halo_lo), (1, self.recv_hi, halo_hi)):
+            for k, (o, idx, cnt, off) in enumerate(runs):
+                if o == self.rank:
+                    pending_self.append((dst, off, idx, cnt))
+                else:
+                    ops.append(dist.P2POp(dist.irecv, dst[off:off + cnt], o, group=self.group,
+                                          tag=which * 64 + k))
+        for peer, idx, cnt, which, k in self.send:
+            if peer != self.rank:
+                ops.append(dist.P2POp(dist.isend, local[idx:idx + cnt], peer, group=self.group, tag=which * 64 + k))
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        for dst, off, idx, cnt in pending_self:
+            dst[off:off + cnt].copy_(local[idx:idx + cnt])
+        for r in reqs:
+            r.wait()
+
+
+class CudaSlabEngine:
+    """Compute engine backed by libnddwt_b200.so (slab entry points of include/nddwt_b200.h)."""
+
+    def __init__(self, local_sizes, global_last, wnames, dtype_code, pres_l2_norm, device_index):
+        from ._lib import Plan
+        self.plan = Plan(local_sizes, wnames, dtype_code, pres_l2_norm, device_index, global_last=global_last)
+        self.device_index = device_index
+
+    def halo_planes(self, level):
+        return self.plan.halo_planes(level)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device_index).cuda_stream
+
+    def dec_level(self, level, a_in, halo_lo, halo_hi, out_bands):
+        self.plan.dec_level_slab(level, a_in.data_ptr(), halo_lo.data_ptr() if halo_lo is not None else None,
+                                 halo_hi.data_ptr() if halo_hi is not None else None,
+                                 [t.data_ptr() for t in out_bands], self._stream())
+
+    def rec_stage1(self, level, in_bands, u_lo, u_hi):
+        self.plan.rec_level_slab_stage1(level, [t.data_ptr() for t in in_bands], u_lo.data_ptr(), u_hi.data_ptr(),
+                                        self._stream())
+
+    def rec_stage2(self, level, u_lo, u_hi, halo_lo, halo_hi, a_out):
+        self.plan.rec_level_slab_stage2(level, u_lo.data_ptr(), u_hi.data_ptr(),
+                                        halo_lo.data_ptr() if halo_lo is not None else None,
+                                        halo_hi.data_ptr() if halo_hi is not None else None, a_out.data_ptr(),
+                                        self._stream())
+
+
+class SlabTransform:
+    """dec / rec of one rank's slab.  Tensors are [n_local, N_{d-1}, ..., N_1] C-contiguous (i.e. the
+    column-major MATLAB array restricted to the rank's planes of the last dim); the coefficient slab
+    is [nb, n_local, ...] with the reference's band order (deepest level first)."""
+
+    def __init__(self, sizes, wnames, level_max, engine, taps_last, rank, world, group=None, device="cpu",
+                 dtype=None):
+        self.sizes = tuple(int(s) for s in sizes)
+        self.d = len(self.sizes)
+        self.rank, self.world, self.group = rank, world, group
+        self.parts = slab_partition(self.sizes[-1], world)
+        self.start, self.n_local = self.parts[rank]
+        self.engine = engine
+        self.L = int(taps_last)
+        self.device, self.dtype = device, dtype
+        self.local_shape = (self.n_local,) + tuple(reversed(self.sizes[:-1]))
+        lo_d, hi_d = self.L // 2 - 1, self.L // 2
+        self.x_dec = HaloExchanger(self.sizes[-1], world, rank, lo_d, hi_d, group)
+        self.x_rec = HaloExchanger(self.sizes[-1], world, rank, self.L // 2, self.L // 2 - 1, group)
+        plane = self.local_shape[1:]
+        mk = lambda n, mult=1: torch.empty((max(n * mult, 1),) + plane, dtype=dtype, device=device)
+        self.h_dec = (mk(lo_d), mk(hi_d))
+        self.h_rec = (mk(self.L // 2, 2), mk(self.L // 2 - 1, 2))     # u_lo planes then u_hi planes
+        self.approx = [torch.empty(self.local_shape, dtype=dtype, device=device) for _ in range(2)]
+        self.u = [torch.empty(self.local_shape, dtype=dtype, device=device) for _ in range(2)]
+
+    def num_bands(self, level):
+        nd = 1 << self.d
+        return nd + (nd - 1) * (level - 1)
+
+    def dec(self, x_local, level, out=None):
+        nd = 1 << self.d
+        nb = self.num_bands(level)
+        if out is None:
+            out = torch.empty((nb,) + self.local_shape, dtype=x_local.dtype, device=x_local.device)
+        a_in = x_local
+        for j in range(1, level + 1):
+            start = (nd - 1) * (level - j)           # slot arithmetic of mex/nddwt.c:209-210,226
+            bands = [None] + [out[start + b] for b in range(1, nd)]
+            bands[0] = out[0] if j == level else self.approx[j & 1]
+            if self.world > 1:
+                self.x_dec.exchange(a_in, self.h_dec[0], self.h_dec[1])
+                self.engine.dec_level(j, a_in, self.h_dec[0], self.h_dec[1], bands)
+            else:
+                self.engine.dec_level(j, a_in, None, None, bands)
+            a_in = bands[0]
+        return out
+
+    def rec(self, coeffs, out=None):
+        nd = 1 << self.d
+        nb = coeffs.shape[0]
+        level = 1 + (nb - nd) // (nd - 1)
+        if out is None:
+            out = torch.empty(self.local_shape, dtype=coeffs.dtype, device=coeffs.device)
+        a = coeffs[0]
+        below, above = self.L // 2, self.L // 2 - 1
+        for j in range(level, 0, -1):
+            start = (nd - 1) * (level - j)
+            bands = [a] + [coeffs[start + b] for b in range(1, nd)]
+            dst = out if j == 1 else self.approx[j & 1]
+            self.engine.rec_stage1(j, bands, self.u[0], self.u[1])
+            if self.world > 1:
+                hl, hh = self.h_rec
+                # u_lo halo planes first, then u_hi (layout of nddwt_rec_level_slab_stage2)
+                self.x_rec.exchange(self.u[0], hl[:below], hh[:above])
+                self.x_rec.exchange(self.u[1], hl[below:2 * below], hh[above:2 * above])
+                self.engine.rec_stage2(j, self.u[0], self.u[1], hl, hh, dst)
+            else:
+                self.engine.rec_stage2(j, self.u[0], self.u[1], None, None, dst)
+            a = dst
+        return out
