@@ -1,0 +1,35 @@
+classdef harr_nddwt_2D
+%HARR_NDDWT_2D  2-D non-decimated Haar transform (== nd_dwt_2D with 'db1') on B200.
+%   obj = harr_nddwt_2D(sizes, 'pres_l2_norm',0|1, 'compute',..., 'precision',...)
+%   Interface of the reference's Functions/harr_nddwt_2D.m.
+    properties
+        f_dec;
+        sizes;
+        f_size;
+        wname;
+        scale;
+        pres_l2_norm;
+        compute;
+        precision;
+    end
+    methods
+        function obj = harr_nddwt_2D(sizes, varargin)
+            obj = nddwt_b200_setup(obj, 2, 'db1', sizes, varargin, {});
+            if obj.pres_l2_norm
+                obj.scale = 1 / 2;
+            else
+                obj.scale = 1 / sqrt(2);
+            end
+        end
+        function y = dec(obj, x, level)
+            if nargin < 3, level = 1; end
+            if level ~= 1
+                error('Only single level decomposition supported for Harr');
+            end
+            y = nddwt_b200_apply(obj, x, 0, level);
+        end
+        function y = rec(obj, x)
+            y = nddwt_b200_apply(obj, x, 1, 0);
+        end
+    end
+end

@@ -1,0 +1,29 @@
+classdef nd_dwt_2D
+%ND_DWT_2D  2-D multi-level non-decimated (periodic) Daubechies wavelet transform on B200.
+%   obj = nd_dwt_2D(wname, sizes, 'pres_l2_norm',0|1, 'compute','mat'|'mex'|'gpu'|'gpu_off', ...
+%                      'precision','double'|'single')
+%   y = obj.dec(x, level);   x = obj.rec(y);
+%   Interface of the reference's Functions/nd_dwt_2D.m; the work is done by libnddwt_b200
+%   (direct separable circular filtering, no FFT, no stored Fourier-domain filters).
+    properties
+        f_dec;          % filter descriptor handed to nd_dwt_mex (wavelet names + sizes)
+        sizes;
+        f_size;
+        wname;
+        pres_l2_norm;
+        compute;
+        precision;
+
+    end
+    methods
+        function obj = nd_dwt_2D(wname, sizes, varargin)
+            obj = nddwt_b200_setup(obj, 2, wname, sizes, varargin, {});
+        end
+        function y = dec(obj, x, level)
+            y = nddwt_b200_apply(obj, x, 0, level);
+        end
+        function y = rec(obj, x)
+            y = nddwt_b200_apply(obj, x, 1, 0);
+        end
+    end
+end
