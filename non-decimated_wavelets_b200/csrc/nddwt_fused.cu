@@ -695,7 +695,11 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp)
     int r_col1[KR];                     // global column where the second segment starts
 #pragma unroll
     for (int k = 0; k < KR; ++k) {
-        const int it = tid + k * NT;
+        // copy index spread round-robin over the warps: the per-lane UBLKCP issue is serialised
+        // inside a warp, so every warp should carry as few copies as possible
+        constexpr int NW = NT / 32;
+        const int slot = tid + k * NT;
+        const int it = (slot % 32) * NW + (slot / 32) % NW + (slot / NT) * NT;
         const int r = it % W2, b = (it < NROWS) ? it / W2 : 0;
         const int grow = wrapi(a2 - HB + r, n2);
         const int gc0 = wrapi(a1 - HBAL, n1);
@@ -710,7 +714,14 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp)
 #pragma unroll
     for (int k = 0; k < KA; ++k) {
         const int it = tid + k * NT;
-        const int c = it % W1, g = it / W1;
+        // warp-aligned mapping: the first 32 columns of every (q, run) group sit on whole warps
+        // (conflict-free shared-memory rows), the W1-32 tail columns of all groups are packed after them
+        int c, g;
+        constexpr int NG = 4 * NRUN, TAIL = W1 - 32;
+        if (W1 > 32 && W1 <= 64) {
+            if (it < NG * 32) { g = it >> 5; c = it & 31; }
+            else { const int tt = it - NG * 32; g = tt / TAIL; c = 32 + tt % TAIL; }
+        } else { c = it % W1; g = it / W1; }
         const int run = g % NRUN, q = (it < NA_ITEMS) ? g / NRUN : 0;
         if (it < NA_ITEMS) a_mask |= 1 << k;
         const int blo = (q & 1) + 4 * (q >> 1);
