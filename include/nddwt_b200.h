@@ -87,6 +87,12 @@ NDDWT_API int nddwt_plan_set_dilations(nddwt_plan *plan, const int *dil, int nle
 NDDWT_API int nddwt_plan_set_kernel_mode(nddwt_plan *plan, int mode);
 /* Number of kernel launches issued by the plan so far (bench.py's gpu_launches). */
 NDDWT_API int64_t nddwt_plan_launch_count(const nddwt_plan *plan);
+/* Per-kernel timing with CUDA events on the launch stream (bench.py's roofline): switch on, run any
+ * number of dec/rec calls, then read the accumulated device time and launch count of one kernel
+ * kind (0 analysis 3-D tile kernel, 1 synthesis 3-D tile kernel, 2 analysis last-dim pass,
+ * 3 synthesis last-dim pass, 4 generic separable pass).  Reading synchronises and clears that kind. */
+NDDWT_API int nddwt_plan_profile(nddwt_plan *plan, int on);
+NDDWT_API int nddwt_plan_kernel_time(nddwt_plan *plan, int kind, double *total_ms, int64_t *count);
 /* 1 if the last dec/rec of this plan ran the fused kernels, 0 if the generic ones. */
 NDDWT_API int nddwt_plan_last_path(const nddwt_plan *plan);
 

@@ -19,6 +19,7 @@ SYMBOLS = [
     "nddwt_last_error", "nddwt_version", "nddwt_wave_filters", "nddwt_num_bands", "nddwt_infer_level",
     "nddwt_plan_create", "nddwt_plan_create_slab", "nddwt_plan_destroy", "nddwt_plan_set_dilations",
     "nddwt_plan_set_kernel_mode", "nddwt_plan_launch_count", "nddwt_plan_last_path",
+    "nddwt_plan_profile", "nddwt_plan_kernel_time",
     "nddwt_dec", "nddwt_rec", "nddwt_dec_host", "nddwt_rec_host",
     "nddwt_halo_planes", "nddwt_dec_level_slab", "nddwt_rec_level_slab_stage1", "nddwt_rec_level_slab_stage2",
 ]
@@ -58,6 +59,8 @@ def lib():
     L.nddwt_plan_launch_count.argtypes = [vp]
     L.nddwt_plan_launch_count.restype = c.c_int64
     L.nddwt_plan_last_path.argtypes = [vp]
+    L.nddwt_plan_profile.argtypes = [vp, c.c_int]
+    L.nddwt_plan_kernel_time.argtypes = [vp, c.c_int, dp, c.POINTER(c.c_int64)]
     L.nddwt_dec.argtypes = [vp, vp, vp, c.c_int, vp]
     L.nddwt_rec.argtypes = [vp, vp, vp, c.c_int, vp]
     L.nddwt_dec_host.argtypes = [vp, vp, vp, c.c_int]
@@ -125,6 +128,15 @@ class Plan:
     @property
     def launches(self):
         return int(lib().nddwt_plan_launch_count(self.handle))
+
+    def profile(self, on):
+        check(lib().nddwt_plan_profile(self.handle, int(bool(on))))
+
+    def kernel_time(self, kind):
+        """(total_ms, launches) of one kernel kind since the last read (0 dec3, 1 rec3, 2 dec_last, 3 rec_last, 4 generic)."""
+        ms, n = ctypes.c_double(0.0), ctypes.c_int64(0)
+        check(lib().nddwt_plan_kernel_time(self.handle, kind, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
 
     @property
     def last_path(self):

@@ -212,6 +212,8 @@ int nddwt_plan_destroy(nddwt_plan *p)
     if (p->host_x) cudaFree(p->host_x);
     if (p->host_c) cudaFree(p->host_c);
     if (p->host_stream) cudaStreamDestroy(p->host_stream);
+    for (size_t i = 0; i < p->timed.size(); ++i) { cudaEventDestroy(p->timed[i].e0); cudaEventDestroy(p->timed[i].e1); }
+    for (size_t i = 0; i < p->event_pool.size(); ++i) cudaEventDestroy(p->event_pool[i]);
     delete p;
     return 0;
 }
@@ -234,6 +236,37 @@ int nddwt_plan_set_kernel_mode(nddwt_plan *p, int mode)
 }
 
 int64_t nddwt_plan_launch_count(const nddwt_plan *p) { return p ? p->launches : 0; }
+
+int nddwt_plan_profile(nddwt_plan *p, int on)
+{
+    if (!p) { set_error("null plan"); return NDDWT_ERR_ARG; }
+    p->profiling = on != 0;
+    return 0;
+}
+
+int nddwt_plan_kernel_time(nddwt_plan *p, int kind, double *total_ms, int64_t *count)
+{
+    if (!p || !total_ms || !count || kind < 0 || kind >= KIND_COUNT) { set_error("bad argument"); return NDDWT_ERR_ARG; }
+    NDDWT_CUDA(cudaSetDevice(p->device));
+    double tot = 0.0;
+    int64_t n = 0;
+    std::vector<nddwt_plan::Timed> keep;
+    for (size_t i = 0; i < p->timed.size(); ++i) {
+        nddwt_plan::Timed &t = p->timed[i];
+        if (t.kind != kind) { keep.push_back(t); continue; }
+        NDDWT_CUDA(cudaEventSynchronize(t.e1));
+        float ms = 0.f;
+        NDDWT_CUDA(cudaEventElapsedTime(&ms, t.e0, t.e1));
+        tot += ms;
+        ++n;
+        p->event_pool.push_back(t.e0);
+        p->event_pool.push_back(t.e1);
+    }
+    p->timed.swap(keep);
+    *total_ms = tot;
+    *count = n;
+    return 0;
+}
 int nddwt_plan_last_path(const nddwt_plan *p) { return p ? p->last_path : 0; }
 
 int nddwt_dec(nddwt_plan *p, const void *x_dev, void *coeffs_dev, int level, void *stream)

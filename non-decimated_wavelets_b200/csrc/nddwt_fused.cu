@@ -19,6 +19,8 @@
 //   complex-single arithmetic is FFMA2 (fma.rn.f32x2) on (re, im) pairs with duplicated taps
 //   taken from the kernel-parameter constant bank.
 #include <cstdlib>
+#include <cstring>
+#include <cuda.h>
 #include "nddwt_plan.h"
 
 namespace nddwt {
@@ -647,13 +649,28 @@ struct GeoRB {
     static constexpr int PU = PUC * VEC;
     static constexpr int PV = 17 * VEC;
     static constexpr int NCH = (R1 + L - 1 + VEC - 1) / VEC;
-    static constexpr size_t RAW_ELEMS = (size_t)8 * W2 * W1S;
+    static constexpr int BP = (int)(((size_t)W2 * W1S * sizeof(T) + 127) / 128 * 128 / sizeof(T));   // band pitch, 128-byte multiple (TMA destination)
+    static constexpr size_t RAW_ELEMS = (size_t)8 * BP;
+    static constexpr uint32_t PLANE_BYTES = (uint32_t)((size_t)8 * W2 * W1S * sizeof(T));
     static constexpr size_t SMEM = (RAW_ELEMS + 4 * T2 * PU + 2 * T2 * PV) * sizeof(T) + 16;
 };
 
+struct TmaMaps {
+    CUtensorMap m[16];      // one 3-D map (n1, n2, planes) per subband array; box = (W1S, W2, 1)
+};
+
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+        : "memory");
+}
+
 template <typename T, int L, int T2, int NT, int R2, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
-k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp)
+k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp, const __grid_constant__ TmaMaps maps)
 {
     using G = GeoRB<T, L, T2>;
     constexpr int VEC = G::VEC, R1 = G::R1, T1 = G::T1, HB = G::HB, HBAL = G::HBAL, SHIFT = G::SHIFT;
@@ -663,7 +680,8 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp)
     constexpr int NB_ITEMS = 2 * 8 * T2, KB = (NB_ITEMS + NT - 1) / NT;
     constexpr int NC_ITEMS = T2 * 16, KC = (NC_ITEMS + NT - 1) / NT;
     constexpr int NROWS = 8 * W2, KR = (NROWS + NT - 1) / NT;       // staged rows per plane
-    constexpr uint32_t PLANE_BYTES = (uint32_t)(G::RAW_ELEMS * sizeof(T));
+    constexpr uint32_t PLANE_BYTES = G::PLANE_BYTES;
+    constexpr int BP = G::BP;
     static_assert(T2 % R2 == 0 && T2 % 8 == 0, "tile rows");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -688,6 +706,10 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp)
     const int bsel = batch / p.nhyp, bhyp = batch - bsel * p.nhyp;
     const int64_t boff = (int64_t)bhyp * p.s4;
 
+    // interior tiles (no periodic wrap inside the haloed box) are staged with ONE tensor TMA per
+    // subband, issued by a single thread; edge tiles fall back to per-row bulk copies
+    const bool use_tma = p.prefetch == 3 && (a1 - HBAL >= 0) && (a1 - HBAL + W1S <= n1) && (a2 - HB >= 0) &&
+                         (a2 - HB + W2 <= n2);
     // ---- hoisted per-thread constants ----
     // row copies: (band b, haloed row r) -> up to two contiguous segments (periodic wrap along dim 1)
     const T *r_src[KR];
@@ -704,7 +726,7 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp)
         const int grow = wrapi(a2 - HB + r, n2);
         const int gc0 = wrapi(a1 - HBAL, n1);
         r_src[k] = p.in[8 * bsel + b] + boff + (int64_t)grow * n1;
-        r_dst[k] = (it < NROWS) ? (b * W2 + r) * W1S : -1;
+        r_dst[k] = (it < NROWS) ? b * BP + r * W1S : -1;
         r_len0[k] = min(W1S, n1 - gc0);
         r_col1[k] = gc0;                // segment 0 starts at gc0, segment 1 (if any) at column 0
     }
@@ -725,7 +747,7 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp)
         const int run = g % NRUN, q = (it < NA_ITEMS) ? g / NRUN : 0;
         if (it < NA_ITEMS) a_mask |= 1 << k;
         const int blo = (q & 1) + 4 * (q >> 1);
-        a_src[k] = (blo * W2 + run * R2) * W1S + SHIFT + c;
+        a_src[k] = blo * BP + run * R2 * W1S + SHIFT + c;
         a_dst[k] = (q * T2 + run * R2) * PU + c;
     }
     int b_src[KB], b_dst[KB];
@@ -767,7 +789,13 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp)
     const int nsteps = (z1 - z0) + L - 1;
     if (tid < 32) { if (tid == 0) mbar_expect_tx(bar, PLANE_BYTES); }
     __syncthreads();
-    {
+    if (use_tma) {
+        if (tid == 0) {
+            const int zp = bhyp * n3 + wrapi(z0 - HB, n3);
+#pragma unroll
+            for (int b = 0; b < 8; ++b) tma_load_3d(RAW + b * BP, &maps.m[8 * bsel + b], a1 - HBAL, a2 - HB, zp, bar);
+        }
+    } else {
         const int64_t zoff = (int64_t)wrapi(z0 - HB, n3) * s3;
 #pragma unroll
         for (int k = 0; k < KR; ++k) {
@@ -796,7 +824,7 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp)
                 for (int i = 0; i < R2; ++i) o[i] = zero_of(T());
 #pragma unroll
                 for (int hb = 0; hb < 2; ++hb) {
-                    const T *src = RAW + a_src[k] + hb * 2 * W2 * W1S;
+                    const T *src = RAW + a_src[k] + hb * 2 * BP;
                     const typename TapOf<T>::type *g = hb ? tp.hi[1] : tp.lo[1];
                     T w[R2 + L - 1];
 #pragma unroll
@@ -816,15 +844,24 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp)
         // ---- stage the next coefficient plane while RB / RC run
         if (t + 1 < nsteps) {
             if (tid == 0) mbar_expect_tx(bar, PLANE_BYTES);
-            const int64_t zoff = (int64_t)wrapi(z0 - HB + t + 1, n3) * s3;
+            if (use_tma) {
+                if (tid == 0) {
+                    const int zp = bhyp * n3 + wrapi(z0 - HB + t + 1, n3);
 #pragma unroll
-            for (int k = 0; k < KR; ++k) {
-                if (r_dst[k] >= 0) {
-                    const T *src = r_src[k] + zoff;
-                    T *dst = RAW + r_dst[k];
-                    const int len0 = r_len0[k];
-                    bulk_g2s(dst, src + r_col1[k], (uint32_t)(len0 * sizeof(T)), bar);
-                    if (len0 < W1S) bulk_g2s(dst + len0, src, (uint32_t)((W1S - len0) * sizeof(T)), bar);
+                    for (int b = 0; b < 8; ++b)
+                        tma_load_3d(RAW + b * BP, &maps.m[8 * bsel + b], a1 - HBAL, a2 - HB, zp, bar);
+                }
+            } else {
+                const int64_t zoff = (int64_t)wrapi(z0 - HB + t + 1, n3) * s3;
+#pragma unroll
+                for (int k = 0; k < KR; ++k) {
+                    if (r_dst[k] >= 0) {
+                        const T *src = r_src[k] + zoff;
+                        T *dst = RAW + r_dst[k];
+                        const int len0 = r_len0[k];
+                        bulk_g2s(dst, src + r_col1[k], (uint32_t)(len0 * sizeof(T)), bar);
+                        if (len0 < W1S) bulk_g2s(dst + len0, src, (uint32_t)((W1S - len0) * sizeof(T)), bar);
+                    }
                 }
             }
         }
@@ -1029,7 +1066,10 @@ static int launch_dec3_v(nddwt_plan *p, const Dec3Params<T> &base, cudaStream_t 
     }
     const FusedTaps<T, L> tp = make_taps<T, L>(p, false);
     const int64_t grid = (int64_t)prm.tiles1 * prm.tiles2 * prm.nchunks * batches;
-    kern<<<(unsigned)grid, NT, G::SMEM, s>>>(prm, tp);
+    {
+        LaunchTimer lt(p, KIND_DEC3, s);
+        kern<<<(unsigned)grid, NT, G::SMEM, s>>>(prm, tp);
+    }
     p->launches++;
     NDDWT_CUDA(cudaGetLastError());
     return 0;
@@ -1127,10 +1167,46 @@ static int launch_rec3_v(nddwt_plan *p, const Rec3Params<T> &base, cudaStream_t 
     }
     const FusedTaps<T, L> tp = make_taps<T, L>(p, true);
     const int64_t grid = (int64_t)prm.tiles1 * prm.tiles2 * prm.nchunks * batches;
-    kern<<<(unsigned)grid, NT, G::SMEM, s>>>(prm, tp);
+    {
+        LaunchTimer lt(p, KIND_REC3, s);
+        kern<<<(unsigned)grid, NT, G::SMEM, s>>>(prm, tp);
+    }
     p->launches++;
     NDDWT_CUDA(cudaGetLastError());
     return 0;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 3-D map over one subband array of 8-byte elements: (n1, n2, planes), box (bw, bh, 1)
+static bool encode_band_map(CUtensorMap *map, const void *base, int n1, int n2, int64_t planes, int bw, int bh)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)n1, (cuuint64_t)n2, (cuuint64_t)planes};
+    const cuuint64_t gstr[2] = {(cuuint64_t)n1 * 8, (cuuint64_t)n1 * n2 * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void *>(base), gdim, gstr, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <typename T, int L, int T2, int NT, int R2, int MINB>
@@ -1144,6 +1220,19 @@ static int launch_rec3_bulk(nddwt_plan *p, const Rec3Params<T> &base, cudaStream
     prm.zc = pick_zc_rec(prm.n3, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB);
     prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
     prm.prefetch = 0;
+    TmaMaps maps;
+    memset(&maps, 0, sizeof maps);
+    {
+        static int use = -1;
+        if (use < 0) { const char *e = getenv("NDDWT_TMA"); use = e ? atoi(e) : 1; }
+        if (use && sizeof(T) == 8 && prm.n1 >= G::W1S && prm.n2 >= G::W2) {
+            const int nb = prm.out[1] ? 16 : 8;
+            bool ok = true;
+            for (int b = 0; b < nb && ok; ++b)
+                ok = encode_band_map(&maps.m[b], prm.in[b], prm.n1, prm.n2, (int64_t)prm.n3 * prm.nhyp, G::W1S, G::W2);
+            if (ok) prm.prefetch = 3;   // kernel flag: tensor maps valid
+        }
+    }
     auto kern = k_rec3_bulk<T, L, T2, NT, R2, MINB>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -1152,7 +1241,10 @@ static int launch_rec3_bulk(nddwt_plan *p, const Rec3Params<T> &base, cudaStream
     }
     const FusedTaps<T, L> tp = make_taps<T, L>(p, true);
     const int64_t grid = (int64_t)prm.tiles1 * prm.tiles2 * prm.nchunks * batches;
-    kern<<<(unsigned)grid, NT, G::SMEM, s>>>(prm, tp);
+    {
+        LaunchTimer lt(p, KIND_REC3, s);
+        kern<<<(unsigned)grid, NT, G::SMEM, s>>>(prm, tp, maps);
+    }
     p->launches++;
     NDDWT_CUDA(cudaGetLastError());
     return 0;
@@ -1243,9 +1335,12 @@ static int launch_dec_last(nddwt_plan *p, const T *in, const LevelIO &io, T *out
     const int64_t nchunks = s4 / VEC;
     const int n4 = (int)p->dims[d];
     const unsigned grid = (unsigned)((nchunks + 255) / 256);
-    k_dec_last<T, L><<<grid, 256, 0, s>>>(in, reinterpret_cast<const T *>(io.halo_lo),
-                                         reinterpret_cast<const T *>(io.halo_hi), out_lo, out_hi, nchunks, n4, s4,
-                                         L / 2 - 1, make_last_taps<T, L>(p, false));
+    {
+        LaunchTimer lt(p, KIND_DEC_LAST, s);
+        k_dec_last<T, L><<<grid, 256, 0, s>>>(in, reinterpret_cast<const T *>(io.halo_lo),
+                                             reinterpret_cast<const T *>(io.halo_hi), out_lo, out_hi, nchunks, n4, s4,
+                                             L / 2 - 1, make_last_taps<T, L>(p, false));
+    }
     p->launches++;
     NDDWT_CUDA(cudaGetLastError());
     return 0;
@@ -1261,9 +1356,12 @@ static int launch_rec_last(nddwt_plan *p, const T *u_lo, const T *u_hi, const Le
     const int64_t nchunks = s4 / VEC;
     const int n4 = (int)p->dims[d];
     const unsigned grid = (unsigned)((nchunks + 255) / 256);
-    k_rec_last<T, L><<<grid, 256, 0, s>>>(u_lo, u_hi, reinterpret_cast<const T *>(io.halo_lo),
-                                         reinterpret_cast<const T *>(io.halo_hi), out, nchunks, n4, s4, L / 2,
-                                         L / 2 - 1, make_last_taps<T, L>(p, true));
+    {
+        LaunchTimer lt(p, KIND_REC_LAST, s);
+        k_rec_last<T, L><<<grid, 256, 0, s>>>(u_lo, u_hi, reinterpret_cast<const T *>(io.halo_lo),
+                                             reinterpret_cast<const T *>(io.halo_hi), out, nchunks, n4, s4, L / 2,
+                                             L / 2 - 1, make_last_taps<T, L>(p, true));
+    }
     p->launches++;
     NDDWT_CUDA(cudaGetLastError());
     return 0;

@@ -119,8 +119,11 @@ static int launch_dec_dim(nddwt_plan *p, int k, int dil, const T *in, const T *h
     dim_geometry(p, k, inner, n, outer);
     const int L = p->L[k];
     const int below = (L / 2 - 1) * dil;
-    k_dec_dim<T><<<grid_for(p->numel), 256, 0, s>>>(in, halo_lo, halo_hi, out_lo, out_hi, inner, n, p->numel, L,
-                                                    dil, below, dec_taps<R>(p).d[k]);
+    {
+        LaunchTimer lt(p, KIND_GENERIC, s);
+        k_dec_dim<T><<<grid_for(p->numel), 256, 0, s>>>(in, halo_lo, halo_hi, out_lo, out_hi, inner, n, p->numel, L,
+                                                        dil, below, dec_taps<R>(p).d[k]);
+    }
     p->launches++;
     NDDWT_CUDA(cudaGetLastError());
     return 0;
@@ -135,8 +138,11 @@ static int launch_rec_dim(nddwt_plan *p, int k, int dil, const T *in_lo, const T
     dim_geometry(p, k, inner, n, outer);
     const int L = p->L[k];
     const int below = (L / 2) * dil, above = (L / 2 - 1) * dil;
-    k_rec_dim<T><<<grid_for(p->numel), 256, 0, s>>>(in_lo, in_hi, halo_lo, halo_hi, out, inner, n, p->numel, L,
-                                                    dil, below, above, rec_taps<R>(p).d[k]);
+    {
+        LaunchTimer lt(p, KIND_GENERIC, s);
+        k_rec_dim<T><<<grid_for(p->numel), 256, 0, s>>>(in_lo, in_hi, halo_lo, halo_hi, out, inner, n, p->numel, L,
+                                                        dil, below, above, rec_taps<R>(p).d[k]);
+    }
     p->launches++;
     NDDWT_CUDA(cudaGetLastError());
     return 0;

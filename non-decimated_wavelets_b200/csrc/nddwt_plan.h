@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 #include "nddwt_common.cuh"
 
 struct nddwt_plan {
@@ -37,6 +38,13 @@ struct nddwt_plan {
     void *host_c = nullptr;
     size_t host_c_bytes = 0;
     cudaStream_t host_stream = nullptr;
+
+    // optional per-kernel CUDA-event timing (nddwt_plan_profile): event pairs recorded on the launch
+    // stream around every kernel, grouped by kind
+    bool profiling = false;
+    struct Timed { int kind; cudaEvent_t e0, e1; };
+    std::vector<Timed> timed;
+    std::vector<cudaEvent_t> event_pool;
 };
 
 namespace nddwt {
@@ -74,5 +82,28 @@ int fused_rec_stage2(nddwt_plan *p, int dil, const void *u_lo, const void *u_hi,
                      cudaStream_t s);
 
 int ensure_scratch(nddwt_plan *p);
+
+// kernel kinds for nddwt_plan_kernel_time
+enum { KIND_DEC3 = 0, KIND_REC3 = 1, KIND_DEC_LAST = 2, KIND_REC_LAST = 3, KIND_GENERIC = 4, KIND_COUNT = 5 };
+
+// RAII event bracket: records (kind, e0, e1) around a launch when profiling is on
+struct LaunchTimer {
+    nddwt_plan *p;
+    cudaStream_t s;
+    cudaEvent_t e1 = nullptr;
+    LaunchTimer(nddwt_plan *plan, int kind, cudaStream_t stream) : p(plan), s(stream)
+    {
+        if (!p->profiling) return;
+        cudaEvent_t ev[2];
+        for (int i = 0; i < 2; ++i) {
+            if (!p->event_pool.empty()) { ev[i] = p->event_pool.back(); p->event_pool.pop_back(); }
+            else cudaEventCreate(&ev[i]);
+        }
+        cudaEventRecord(ev[0], s);
+        e1 = ev[1];
+        p->timed.push_back({kind, ev[0], ev[1]});
+    }
+    ~LaunchTimer() { if (e1) cudaEventRecord(e1, s); }
+};
 
 }  // namespace nddwt
