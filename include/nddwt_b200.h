@@ -130,6 +130,16 @@ NDDWT_API int nddwt_dec_level_slab(nddwt_plan *plan, int level_index, const void
                          const void *halo_lo, const void *halo_hi,
                          void *const *out_bands, void *stream);
 
+/* The same level in parts, so that the caller can overlap the halo exchange of the NEXT level with
+ * compute (part 0 = whole level; 1 = the last-dim pass, the only one that reads the halos;
+ * 2 = the tile pass that produces bands 0..2^(d-1)-1, including the approximation band the next
+ * level's exchange needs; 3 = the tile pass for the remaining bands).  On plans without a
+ * separable fused path part 1 runs the whole level and parts 2/3 are no-ops. */
+/* 1 when the part-wise calls below really split the level (fused 4-D path), else 0. */
+NDDWT_API int nddwt_plan_is_separable(const nddwt_plan *plan);
+NDDWT_API int nddwt_dec_level_slab_part(nddwt_plan *plan, int level_index, int part, const void *a_in,
+                              const void *halo_lo, const void *halo_hi, void *const *out_bands, void *stream);
+
 /* One synthesis level, split at the slab dimension (the adjoint of the analysis exchange):
  *  stage 1 (local):  u_lo/u_hi[local planes] = synthesis over dims 1..d-1 of the 2^d bands,
  *                    summed over their band bits (no halo needed);
@@ -138,6 +148,10 @@ NDDWT_API int nddwt_dec_level_slab(nddwt_plan *plan, int level_index, const void
  *                    u_lo planes then u_hi planes, each group ascending). */
 NDDWT_API int nddwt_rec_level_slab_stage1(nddwt_plan *plan, int level_index, const void *const *in_bands,
                                 void *u_lo, void *u_hi, void *stream);
+/* stage 1 in halves: part 0 = both; 1 = u_lo (bands 0..2^(d-1)-1, needs the approximation band);
+ * 2 = u_hi (pure detail bands -- can run before the previous level has finished). */
+NDDWT_API int nddwt_rec_level_slab_stage1_part(nddwt_plan *plan, int level_index, int part,
+                                     const void *const *in_bands, void *u_lo, void *u_hi, void *stream);
 NDDWT_API int nddwt_rec_level_slab_stage2(nddwt_plan *plan, int level_index, const void *u_lo, const void *u_hi,
                                 const void *halo_lo, const void *halo_hi, void *a_out, void *stream);
 

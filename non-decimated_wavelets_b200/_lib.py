@@ -21,7 +21,7 @@ SYMBOLS = [
     "nddwt_plan_set_kernel_mode", "nddwt_plan_launch_count", "nddwt_plan_last_path",
     "nddwt_plan_profile", "nddwt_plan_kernel_time",
     "nddwt_dec", "nddwt_rec", "nddwt_dec_host", "nddwt_rec_host",
-    "nddwt_halo_planes", "nddwt_dec_level_slab", "nddwt_rec_level_slab_stage1", "nddwt_rec_level_slab_stage2",
+    "nddwt_halo_planes", "nddwt_dec_level_slab", "nddwt_plan_is_separable", "nddwt_dec_level_slab_part", "nddwt_rec_level_slab_stage1_part", "nddwt_rec_level_slab_stage1", "nddwt_rec_level_slab_stage2",
 ]
 
 _lib = None
@@ -67,6 +67,9 @@ def lib():
     L.nddwt_rec_host.argtypes = [vp, vp, vp, c.c_int]
     L.nddwt_halo_planes.argtypes = [vp, c.c_int, ip, ip]
     L.nddwt_dec_level_slab.argtypes = [vp, c.c_int, vp, vp, vp, c.POINTER(vp), vp]
+    L.nddwt_plan_is_separable.argtypes = [vp]
+    L.nddwt_dec_level_slab_part.argtypes = [vp, c.c_int, c.c_int, vp, vp, vp, c.POINTER(vp), vp]
+    L.nddwt_rec_level_slab_stage1_part.argtypes = [vp, c.c_int, c.c_int, c.POINTER(vp), vp, vp, vp]
     L.nddwt_rec_level_slab_stage1.argtypes = [vp, c.c_int, c.POINTER(vp), vp, vp, vp]
     L.nddwt_rec_level_slab_stage2.argtypes = [vp, c.c_int, vp, vp, vp, vp, vp, vp]
     _lib = L
@@ -129,6 +132,10 @@ class Plan:
     def launches(self):
         return int(lib().nddwt_plan_launch_count(self.handle))
 
+    @property
+    def separable(self):
+        return bool(lib().nddwt_plan_is_separable(self.handle))
+
     def profile(self, on):
         check(lib().nddwt_plan_profile(self.handle, int(bool(on))))
 
@@ -162,6 +169,14 @@ class Plan:
     def dec_level_slab(self, level_index, a_in, halo_lo, halo_hi, out_ptrs, stream=0):
         arr = (ctypes.c_void_p * len(out_ptrs))(*out_ptrs)
         check(lib().nddwt_dec_level_slab(self.handle, level_index, a_in, halo_lo, halo_hi, arr, stream))
+
+    def dec_level_slab_part(self, level_index, part, a_in, halo_lo, halo_hi, out_ptrs, stream=0):
+        arr = (ctypes.c_void_p * len(out_ptrs))(*out_ptrs)
+        check(lib().nddwt_dec_level_slab_part(self.handle, level_index, part, a_in, halo_lo, halo_hi, arr, stream))
+
+    def rec_level_slab_stage1_part(self, level_index, part, in_ptrs, u_lo, u_hi, stream=0):
+        arr = (ctypes.c_void_p * len(in_ptrs))(*in_ptrs)
+        check(lib().nddwt_rec_level_slab_stage1_part(self.handle, level_index, part, arr, u_lo, u_hi, stream))
 
     def rec_level_slab_stage1(self, level_index, in_ptrs, u_lo, u_hi, stream=0):
         arr = (ctypes.c_void_p * len(in_ptrs))(*in_ptrs)

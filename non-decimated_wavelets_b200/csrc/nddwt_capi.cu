@@ -410,6 +410,45 @@ int nddwt_dec_level_slab(nddwt_plan *p, int level_index, const void *a_in, const
     return dec_level(p, p->dil[level_index - 1], a_in, io, out_bands, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int nddwt_plan_is_separable(const nddwt_plan *p) { return (p && fused_is_separable(p)) ? 1 : 0; }
+
+int nddwt_dec_level_slab_part(nddwt_plan *p, int level_index, int part, const void *a_in, const void *halo_lo,
+                              const void *halo_hi, void *const *out_bands, void *stream)
+{
+    int rc = check_level(p, level_index);
+    if (rc) return rc;
+    if (!a_in || !out_bands || part < 0 || part > 3) { set_error("bad argument"); return NDDWT_ERR_ARG; }
+    NDDWT_CUDA(cudaSetDevice(p->device));
+    LevelIO io;
+    io.halo_lo = halo_lo;
+    io.halo_hi = halo_hi;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (p->kernel_mode == 0) {
+        rc = fused_dec_level_part(p, p->dil[level_index - 1], part, a_in, io, out_bands, s);
+        if (rc <= 0) { p->last_path = 1; return rc; }
+    }
+    // no separable parts on this plan: the whole level runs as part 0/1, parts 2 and 3 are no-ops
+    if (part >= 2) return 0;
+    return dec_level(p, p->dil[level_index - 1], a_in, io, out_bands, s);
+}
+
+int nddwt_rec_level_slab_stage1_part(nddwt_plan *p, int level_index, int part, const void *const *in_bands,
+                                     void *u_lo, void *u_hi, void *stream)
+{
+    int rc = check_level(p, level_index);
+    if (rc) return rc;
+    if (!in_bands || !u_lo || !u_hi || part < 0 || part > 2) { set_error("bad argument"); return NDDWT_ERR_ARG; }
+    NDDWT_CUDA(cudaSetDevice(p->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (p->kernel_mode == 0) {
+        rc = fused_rec_stage1(p, p->dil[level_index - 1], in_bands, u_lo, u_hi, s, part);
+        if (rc <= 0) { p->last_path = 1; return rc; }
+    }
+    if (part == 2) return 0;   // not separable: everything is done by part 0/1
+    p->last_path = 0;
+    return generic_rec_stage1(p, p->dil[level_index - 1], in_bands, u_lo, u_hi, s);
+}
+
 int nddwt_rec_level_slab_stage1(nddwt_plan *p, int level_index, const void *const *in_bands, void *u_lo,
                                 void *u_hi, void *stream)
 {

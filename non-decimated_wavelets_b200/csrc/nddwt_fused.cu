@@ -350,6 +350,7 @@ struct Rec3Params {
     int nhyp;
     int tiles1, tiles2, zc, nchunks;
     int prefetch;       // 0 none, 1 prefetch.global.L1 of the next plane's footprint, 2 prefetch.global.L2
+    int cl1, cl2;       // thread-block cluster shape in tiles (cl1 x cl2 CTAs, 1 x 1 = no cluster)
 };
 
 template <typename T, int L, int T2>
@@ -691,11 +692,19 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp, const __grid_consta
     uint64_t *bar = reinterpret_cast<uint64_t *>(SV + 2 * T2 * PV);
 
     const int tid = threadIdx.x;
+    // CTAs of one cluster (cl1 x cl2 neighbouring tiles) are consecutive block ids; they march in
+    // lockstep (split-phase cluster barrier per plane) so that halo rows/columns shared between
+    // neighbouring tiles are fetched from DRAM once and hit L2 for the neighbours
     int bid = blockIdx.x;
-    const int t1 = bid % p.tiles1;
-    bid /= p.tiles1;
-    const int t2 = bid % p.tiles2;
-    bid /= p.tiles2;
+    const int csz = p.cl1 * p.cl2;
+    const int crank = bid % csz;
+    bid /= csz;
+    const int ct1 = p.tiles1 / p.cl1;
+    const int t1 = (bid % ct1) * p.cl1 + crank % p.cl1;
+    bid /= ct1;
+    const int ct2 = p.tiles2 / p.cl2;
+    const int t2 = (bid % ct2) * p.cl2 + crank / p.cl1;
+    bid /= ct2;
     const int chunk = bid % p.nchunks;
     const int batch = bid / p.nchunks;
     const int a1 = t1 * T1, a2 = t2 * T2;
@@ -814,6 +823,7 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp, const __grid_consta
     for (int t = 0; t < nsteps; ++t) {
         mbar_wait(bar, parity);
         parity ^= 1;
+        if (csz > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 
         // ---- stage RA: dim 2 out of the staged tiles
 #pragma unroll
@@ -904,6 +914,7 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp, const __grid_consta
             }
         }
         u = (u + 1 == L) ? 0 : u + 1;
+        if (csz > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
     }
 }
 
@@ -1220,6 +1231,7 @@ static int launch_rec3_bulk(nddwt_plan *p, const Rec3Params<T> &base, cudaStream
     prm.zc = pick_zc_rec(prm.n3, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB);
     prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
     prm.prefetch = 0;
+    prm.cl1 = prm.cl2 = 1;
     TmaMaps maps;
     memset(&maps, 0, sizeof maps);
     {
@@ -1242,8 +1254,29 @@ static int launch_rec3_bulk(nddwt_plan *p, const Rec3Params<T> &base, cudaStream
     const FusedTaps<T, L> tp = make_taps<T, L>(p, true);
     const int64_t grid = (int64_t)prm.tiles1 * prm.tiles2 * prm.nchunks * batches;
     {
+        static int cl = -1;
+        if (cl < 0) { const char *e = getenv("NDDWT_CLUSTER"); cl = e ? atoi(e) : 1; }   // measured: lockstep clusters do not pay (profiles/)
+        prm.cl1 = 1;
+        prm.cl2 = 1;
+        if (cl == 8 && prm.tiles1 % 2 == 0 && prm.tiles2 % 4 == 0) { prm.cl1 = 2; prm.cl2 = 4; }
+        else if (cl >= 4 && prm.tiles2 % 4 == 0) { prm.cl1 = 1; prm.cl2 = 4; }
+        else if (cl >= 2 && prm.tiles2 % 2 == 0) { prm.cl1 = 1; prm.cl2 = 2; }
+    }
+    {
         LaunchTimer lt(p, KIND_REC3, s);
-        kern<<<(unsigned)grid, NT, G::SMEM, s>>>(prm, tp, maps);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(NT);
+        cfg.dynamicSmemBytes = G::SMEM;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)(prm.cl1 * prm.cl2);
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        NDDWT_CUDA(cudaLaunchKernelEx(&cfg, kern, prm, tp, maps));
     }
     p->launches++;
     NDDWT_CUDA(cudaGetLastError());
@@ -1367,38 +1400,58 @@ static int launch_rec_last(nddwt_plan *p, const T *u_lo, const T *u_hi, const Le
     return 0;
 }
 
+// part: 0 = whole level; 1 = dim-4 pass only (the one that needs the slab halos);
+//       2 = tile pass on the lo4 half (bands 0..7, incl. the approximation); 3 = tile pass on the hi4 half
 template <typename T, int L>
-static int dec4_level(nddwt_plan *p, const void *a_in, const LevelIO &io, void *const *out_bands, cudaStream_t s)
+static int dec4_level(nddwt_plan *p, const void *a_in, const LevelIO &io, void *const *out_bands, cudaStream_t s,
+                      int part = 0)
 {
     const size_t band_bytes = (size_t)p->numel * p->esize;
     int rc = ensure_fused_scratch(p, 2 * band_bytes);
     if (rc) return rc;
     T *lo4 = reinterpret_cast<T *>(p->fused_scratch);
     T *hi4 = lo4 + p->numel;
-    rc = launch_dec_last<T, L>(p, reinterpret_cast<const T *>(a_in), io, lo4, hi4, s);
-    if (rc) return rc;
+    if (part == 0 || part == 1) {
+        rc = launch_dec_last<T, L>(p, reinterpret_cast<const T *>(a_in), io, lo4, hi4, s);
+        if (rc || part == 1) return rc;
+    }
     Dec3Params<T> prm;
-    prm.in[0] = lo4;
-    prm.in[1] = hi4;
     prm.halo_lo = nullptr;
     prm.halo_hi = nullptr;
-    for (int b = 0; b < 16; ++b) prm.out[b] = reinterpret_cast<T *>(out_bands[b]);
     prm.n1 = (int)p->dims[0];
     prm.n2 = (int)p->dims[1];
     prm.n3 = (int)p->dims[2];
     prm.s3 = p->dims[0] * p->dims[1];
     prm.s4 = prm.s3 * p->dims[2];
     prm.nhyp = (int)p->dims[3];
+    if (part == 0) {
+        prm.in[0] = lo4;
+        prm.in[1] = hi4;
+        for (int b = 0; b < 16; ++b) prm.out[b] = reinterpret_cast<T *>(out_bands[b]);
+    } else {
+        prm.in[0] = (part == 2) ? lo4 : hi4;
+        prm.in[1] = nullptr;
+        for (int b = 0; b < 8; ++b) prm.out[b] = reinterpret_cast<T *>(out_bands[b + (part == 2 ? 0 : 8)]);
+        for (int b = 8; b < 16; ++b) prm.out[b] = nullptr;
+    }
     return launch_dec3_v<T, L, 16, 256, 2, 2>(p, prm, s);
 }
 
+// part: 0 = both halves; 1 = u_lo half (bands 0..7, needs the approximation band); 2 = u_hi half (bands 8..15)
 template <typename T, int L>
-static int rec4_stage1(nddwt_plan *p, const void *const *in_bands, T *u_lo, T *u_hi, cudaStream_t s)
+static int rec4_stage1(nddwt_plan *p, const void *const *in_bands, T *u_lo, T *u_hi, cudaStream_t s, int part = 0)
 {
     Rec3Params<T> prm;
-    for (int b = 0; b < 16; ++b) prm.in[b] = reinterpret_cast<const T *>(in_bands[b]);
-    prm.out[0] = u_lo;
-    prm.out[1] = u_hi;
+    if (part == 0) {
+        for (int b = 0; b < 16; ++b) prm.in[b] = reinterpret_cast<const T *>(in_bands[b]);
+        prm.out[0] = u_lo;
+        prm.out[1] = u_hi;
+    } else {
+        for (int b = 0; b < 8; ++b) prm.in[b] = reinterpret_cast<const T *>(in_bands[b + (part == 1 ? 0 : 8)]);
+        for (int b = 8; b < 16; ++b) prm.in[b] = nullptr;
+        prm.out[0] = (part == 1) ? u_lo : u_hi;
+        prm.out[1] = nullptr;
+    }
     prm.n1 = (int)p->dims[0];
     prm.n2 = (int)p->dims[1];
     prm.n3 = (int)p->dims[2];
@@ -1433,9 +1486,10 @@ static int rec4_level(nddwt_plan *p, const void *const *in_bands, void *a_out, c
     }
 
 template <typename T>
-static int dispatch_dec4(nddwt_plan *p, const void *a_in, const LevelIO &io, void *const *out_bands, cudaStream_t s)
+static int dispatch_dec4(nddwt_plan *p, const void *a_in, const LevelIO &io, void *const *out_bands, cudaStream_t s,
+                         int part = 0)
 {
-    NDDWT_L_SWITCH(p->L[0], (dec4_level<T, LL>(p, a_in, io, out_bands, s)));
+    NDDWT_L_SWITCH(p->L[0], (dec4_level<T, LL>(p, a_in, io, out_bands, s, part)));
 }
 template <typename T>
 static int dispatch_rec4(nddwt_plan *p, const void *const *in_bands, void *a_out, cudaStream_t s)
@@ -1443,9 +1497,10 @@ static int dispatch_rec4(nddwt_plan *p, const void *const *in_bands, void *a_out
     NDDWT_L_SWITCH(p->L[0], (rec4_level<T, LL>(p, in_bands, a_out, s)));
 }
 template <typename T>
-static int dispatch_rec4_stage1(nddwt_plan *p, const void *const *in_bands, void *u_lo, void *u_hi, cudaStream_t s)
+static int dispatch_rec4_stage1(nddwt_plan *p, const void *const *in_bands, void *u_lo, void *u_hi, cudaStream_t s,
+                                int part = 0)
 {
-    NDDWT_L_SWITCH(p->L[0], (rec4_stage1<T, LL>(p, in_bands, reinterpret_cast<T *>(u_lo), reinterpret_cast<T *>(u_hi), s)));
+    NDDWT_L_SWITCH(p->L[0], (rec4_stage1<T, LL>(p, in_bands, reinterpret_cast<T *>(u_lo), reinterpret_cast<T *>(u_hi), s, part)));
 }
 template <typename T>
 static int dispatch_rec_last(nddwt_plan *p, const void *u_lo, const void *u_hi, const LevelIO &io, void *a_out,
@@ -1474,10 +1529,27 @@ static bool fused_geometry_ok(const nddwt_plan *p)
         default: return 1;                                         \
     }
 
-int fused_rec_stage1(nddwt_plan *p, int dil, const void *const *in_bands, void *u_lo, void *u_hi, cudaStream_t s)
+int fused_rec_stage1(nddwt_plan *p, int dil, const void *const *in_bands, void *u_lo, void *u_hi, cudaStream_t s,
+                     int part)
 {
     if (dil != 1 || !uniform_taps(p) || p->ndims != 4 || !fused_geometry_ok(p)) return 1;
-    NDDWT_T_SWITCH(p, (dispatch_rec4_stage1<TT>(p, in_bands, u_lo, u_hi, s)));
+    NDDWT_T_SWITCH(p, (dispatch_rec4_stage1<TT>(p, in_bands, u_lo, u_hi, s, part)));
+}
+
+bool fused_is_separable(const nddwt_plan *p)
+{
+    if (p->kernel_mode != 0 || p->ndims != 4 || !uniform_taps(p) || !fused_geometry_ok(p)) return false;
+    for (int j = 0; j < NDDWT_MAX_LEVELS; ++j)
+        if (p->dil[j] != 1) return false;
+    return p->L[0] == 2 || p->L[0] == 4 || p->L[0] == 6 || p->L[0] == 8;
+}
+
+// 4-D analysis level in parts (multi-GPU overlap); returns 1 when the plan has no fused 4-D path
+int fused_dec_level_part(nddwt_plan *p, int dil, int part, const void *a_in, const LevelIO &io,
+                         void *const *out_bands, cudaStream_t s)
+{
+    if (dil != 1 || !uniform_taps(p) || p->ndims != 4 || !fused_geometry_ok(p)) return 1;
+    NDDWT_T_SWITCH(p, (dispatch_dec4<TT>(p, a_in, io, out_bands, s, part)));
 }
 
 int fused_rec_stage2(nddwt_plan *p, int dil, const void *u_lo, const void *u_hi, const LevelIO &io, void *a_out,

@@ -77,10 +77,14 @@ int generic_rec_stage2(nddwt_plan *p, int dil, const void *u_lo, const void *u_h
 int fused_dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io,
                     void *const *out_bands, cudaStream_t s);
 int fused_rec_level(nddwt_plan *p, int dil, const void *const *in_bands, void *a_out, cudaStream_t s);
-int fused_rec_stage1(nddwt_plan *p, int dil, const void *const *in_bands, void *u_lo, void *u_hi, cudaStream_t s);
+int fused_rec_stage1(nddwt_plan *p, int dil, const void *const *in_bands, void *u_lo, void *u_hi, cudaStream_t s,
+                     int part = 0);
+int fused_dec_level_part(nddwt_plan *p, int dil, int part, const void *a_in, const LevelIO &io,
+                         void *const *out_bands, cudaStream_t s);
 int fused_rec_stage2(nddwt_plan *p, int dil, const void *u_lo, const void *u_hi, const LevelIO &io, void *a_out,
                      cudaStream_t s);
 
+bool fused_is_separable(const nddwt_plan *p);
 int ensure_scratch(nddwt_plan *p);
 
 // kernel kinds for nddwt_plan_kernel_time

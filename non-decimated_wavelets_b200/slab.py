@@ -115,6 +115,7 @@ class CudaSlabEngine:
         from ._lib import Plan
         self.plan = Plan(local_sizes, wnames, dtype_code, pres_l2_norm, device_index, global_last=global_last)
         self.device_index = device_index
+        self.separable = self.plan.separable    # levels can be issued in parts (overlap with the exchange)
 
     def halo_planes(self, level):
         return self.plan.halo_planes(level)
@@ -130,6 +131,15 @@ class CudaSlabEngine:
     def rec_stage1(self, level, in_bands, u_lo, u_hi):
         self.plan.rec_level_slab_stage1(level, [t.data_ptr() for t in in_bands], u_lo.data_ptr(), u_hi.data_ptr(),
                                         self._stream())
+
+    # part-wise entry points (overlap of the halo exchange with compute, see SlabTransform._dec_overlapped)
+    def dec_level_part(self, level, part, a_in, halo_lo, halo_hi, out_bands):
+        self.plan.dec_level_slab_part(level, part, a_in.data_ptr(), halo_lo.data_ptr(), halo_hi.data_ptr(),
+                                      [t.data_ptr() for t in out_bands], self._stream())
+
+    def rec_stage1_part(self, level, part, in_bands, u_lo, u_hi):
+        self.plan.rec_level_slab_stage1_part(level, part, [t.data_ptr() for t in in_bands], u_lo.data_ptr(),
+                                             u_hi.data_ptr(), self._stream())
 
     def rec_stage2(self, level, u_lo, u_hi, halo_lo, halo_hi, a_out):
         self.plan.rec_level_slab_stage2(level, u_lo.data_ptr(), u_hi.data_ptr(),
@@ -163,16 +173,90 @@ class SlabTransform:
         self.h_rec = (mk(self.L // 2, 2), mk(self.L // 2 - 1, 2))     # u_lo planes then u_hi planes
         self.approx = [torch.empty(self.local_shape, dtype=dtype, device=device) for _ in range(2)]
         self.u = [torch.empty(self.local_shape, dtype=dtype, device=device) for _ in range(2)]
+        # overlap of exchange and compute: needs the part-wise engine entry points, CUDA tensors and >1 rank
+        self.overlap = (world > 1 and getattr(engine, "separable", False) and torch.device(device).type == "cuda")
+        if self.overlap:
+            self.comm_stream = torch.cuda.Stream(device=device)
+            self.u_hi2 = [self.u[1], torch.empty(self.local_shape, dtype=dtype, device=device)]
+            self.h_rec2 = [self.h_rec, (mk(self.L // 2, 2), mk(self.L // 2 - 1, 2))]
 
     def num_bands(self, level):
         nd = 1 << self.d
         return nd + (nd - 1) * (level - 1)
+
+    # ---- overlapped schedules (multi-GPU): the exchange of the next level's halos runs on a side
+    # stream while the tile pass for the bands that do not feed it is still computing ----------
+    def _dec_overlapped(self, x_local, level, out):
+        nd = 1 << self.d
+        cur = torch.cuda.current_stream(x_local.device)
+        comm = self.comm_stream
+        hl, hh = self.h_dec
+        comm.wait_stream(cur)
+        with torch.cuda.stream(comm):
+            self.x_dec.exchange(x_local, hl, hh)
+        a_in = x_local
+        for j in range(1, level + 1):
+            start = (nd - 1) * (level - j)
+            bands = [None] + [out[start + b] for b in range(1, nd)]
+            bands[0] = out[0] if j == level else self.approx[j & 1]
+            cur.wait_stream(comm)                                   # halos of a_in have arrived
+            self.engine.dec_level_part(j, 1, a_in, hl, hh, bands)   # last-dim pass (reads the halos)
+            self.engine.dec_level_part(j, 2, a_in, hl, hh, bands)   # bands 0..nd/2-1, incl. the approximation
+            if j < level:
+                comm.wait_stream(cur)
+                with torch.cuda.stream(comm):
+                    self.x_dec.exchange(bands[0], hl, hh)           # next level's halos, overlapped with ...
+            self.engine.dec_level_part(j, 3, a_in, hl, hh, bands)   # ... the remaining detail bands
+            a_in = bands[0]
+        return out
+
+    def _rec_overlapped(self, coeffs, out):
+        nd = 1 << self.d
+        nb = coeffs.shape[0]
+        level = 1 + (nb - nd) // (nd - 1)
+        cur = torch.cuda.current_stream(coeffs.device)
+        comm = self.comm_stream
+        below, above = self.L // 2, self.L // 2 - 1
+        u_lo = self.u[0]
+
+        def bands_of(j, a):
+            start = (nd - 1) * (level - j)
+            return [a] + [coeffs[start + b] for b in range(1, nd)]
+
+        def stage1b(j):      # detail-only half: independent of the previous level's result
+            k = j & 1
+            self.engine.rec_stage1_part(j, 2, bands_of(j, coeffs[0]), u_lo, self.u_hi2[k])
+            comm.wait_stream(cur)
+            with torch.cuda.stream(comm):
+                hl, hh = self.h_rec2[k]
+                self.x_rec.exchange(self.u_hi2[k], hl[below:2 * below], hh[above:2 * above])
+
+        a = coeffs[0]
+        stage1b(level)
+        for j in range(level, 0, -1):
+            k = j & 1
+            hl, hh = self.h_rec2[k]
+            dst = out if j == 1 else self.approx[j & 1]
+            self.engine.rec_stage1_part(j, 1, bands_of(j, a), u_lo, self.u_hi2[k])
+            comm.wait_stream(cur)
+            with torch.cuda.stream(comm):
+                self.x_rec.exchange(u_lo, hl[:below], hh[:above])
+                ev = torch.cuda.Event()
+                ev.record(comm)
+            if j > 1:
+                stage1b(j - 1)                                       # overlaps with the u_lo exchange of level j
+            cur.wait_event(ev)
+            self.engine.rec_stage2(j, u_lo, self.u_hi2[k], hl, hh, dst)
+            a = dst
+        return out
 
     def dec(self, x_local, level, out=None):
         nd = 1 << self.d
         nb = self.num_bands(level)
         if out is None:
             out = torch.empty((nb,) + self.local_shape, dtype=x_local.dtype, device=x_local.device)
+        if self.overlap:
+            return self._dec_overlapped(x_local, level, out)
         a_in = x_local
         for j in range(1, level + 1):
             start = (nd - 1) * (level - j)           # slot arithmetic of mex/nddwt.c:209-210,226
@@ -192,6 +276,8 @@ class SlabTransform:
         level = 1 + (nb - nd) // (nd - 1)
         if out is None:
             out = torch.empty(self.local_shape, dtype=coeffs.dtype, device=coeffs.device)
+        if self.overlap:
+            return self._rec_overlapped(coeffs, out)
         a = coeffs[0]
         below, above = self.L // 2, self.L // 2 - 1
         for j in range(level, 0, -1):
