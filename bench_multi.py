@@ -29,7 +29,8 @@ def run_multi(args, wl_name, wl):
     os.environ.setdefault("MASTER_PORT", "29511")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)   # NCCL kernels must not queue behind the tile kernels
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, pg_options=opts)
 
     wn = [wname] * d
     L = len(nd.wave_filters(wname)[0])

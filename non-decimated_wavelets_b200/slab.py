@@ -90,6 +90,9 @@ class HaloExchanger:
     def exchange(self, local, halo_lo, halo_hi):
         """local: [n_local, ...] contiguous; halo_lo: [below, ...]; halo_hi: [above, ...] (filled in place).
         Planes a rank needs from itself are copied locally."""
+        import os
+        if os.environ.get("NDDWT_SLAB_NOCOMM") == "1":     # timing experiment only (results are wrong)
+            return
         ops, pending_self = [], []
         for which, runs, dst in ((0, self.recv_lo, halo_lo), (1, self.recv_hi, halo_hi)):
             for k, (o, idx, cnt, off) in enumerate(runs):
@@ -174,9 +177,11 @@ class SlabTransform:
         self.approx = [torch.empty(self.local_shape, dtype=dtype, device=device) for _ in range(2)]
         self.u = [torch.empty(self.local_shape, dtype=dtype, device=device) for _ in range(2)]
         # overlap of exchange and compute: needs the part-wise engine entry points, CUDA tensors and >1 rank
-        self.overlap = (world > 1 and getattr(engine, "separable", False) and torch.device(device).type == "cuda")
+        import os
+        self.overlap = (world > 1 and getattr(engine, "separable", False) and torch.device(device).type == "cuda"
+                        and os.environ.get("NDDWT_SLAB_OVERLAP", "1") != "0")
         if self.overlap:
-            self.comm_stream = torch.cuda.Stream(device=device)
+            self.comm_stream = torch.cuda.Stream(device=device, priority=-1)
             self.u_hi2 = [self.u[1], torch.empty(self.local_shape, dtype=dtype, device=device)]
             self.h_rec2 = [self.h_rec, (mk(self.L // 2, 2), mk(self.L // 2 - 1, 2))]
 

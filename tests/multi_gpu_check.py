@@ -26,7 +26,8 @@ def main():
     lr = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(lr)
     dev = torch.device("cuda", lr)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)   # NCCL kernels must not queue behind the tile kernels
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, pg_options=opts)
     worst = 0.0
     cases = [((32, 24, 16, 16), "db4", 3, 0), ((32, 24, 16, 4 * world), "db4", 2, 1), ((64, 32, 24), "db4", 2, 0),
              ((40, 20, 12, 2 * world + 1), "db2", 2, 0), ((32, 16, 8, 3 * world), "db1", 2, 1)]
