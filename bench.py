@@ -292,8 +292,18 @@ def main():
     pair_bytes = 2 * (1 + nb) * nvox * esize
     pair_gbs = pair_bytes / (ms_per_step * 1e-3) / 1e9
     step_kernel_ms = sum(t for t, _ in ktimes.values()) / args.steps
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu capture of this command
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_launch_summary_%s.json" % wl_name)))
+        key = {0: "k_dec3", 1: "k_rec3", 2: "k_dec_last", 3: "k_rec_last"}.get(dom, "?")
+        for name, rec in prof["kernels"].items():
+            if key in name:
+                traffic = (rec["dram_read_GB"] + rec["dram_write_GB"]) * 1e9
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": kinds[dom], "kernel_ms": k_ms,
+                "traffic": traffic, "kernel": kinds[dom], "kernel_ms": k_ms,
                 "kernel_share_of_step": ktimes[dom][0] / args.steps / step_kernel_ms,
                 "algorithmic_bytes_per_launch": alg_bytes_level, "peak_source": peak_src,
                 "all_kernels": {kinds[k]: {"ms_per_launch": t / c, "launches_per_step": c / args.steps,

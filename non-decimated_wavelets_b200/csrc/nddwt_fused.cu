@@ -159,7 +159,7 @@ struct DispatchA<T, L, PPT, L> {
                                                const int (&)[PPT], int, const T *) {}
 };
 
-template <typename T, int L, int T2, int NT, int R2, int MINB>
+template <typename T, int L, int T2, int NT, int R2, int MINB, int CWSEL = 0>
 __global__ void __launch_bounds__(NT, MINB)
 k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
 {
@@ -169,7 +169,9 @@ k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
     constexpr int PPT = (NPOS + NT - 1) / NT;
     constexpr int NRUN = T2 / R2;
     constexpr int NB_ITEMS = 2 * 8 * W2P, KB = (NB_ITEMS + NT - 1) / NT;
-    constexpr int NC_ITEMS = 4 * NRUN * 16, KC = (NC_ITEMS + NT - 1) / NT;
+    constexpr int CW = (CWSEL == 1) ? 1 : VEC;              // columns per stage-C item (16-byte chunk or one element)
+    constexpr int CPR = T1 / CW;                            // stage-C items per row
+    constexpr int NC_ITEMS = 4 * NRUN * CPR, KC = (NC_ITEMS + NT - 1) / NT;
     static_assert(T2 % R2 == 0, "R2 must divide T2");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -233,10 +235,10 @@ k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
         const int it = tid + k * NT;
-        const int cp = it & 15, rest = it >> 4;
+        const int cp = it % CPR, rest = it / CPR;
         const int run = rest % NRUN, m = rest / NRUN;
-        c_src[k] = (m * W2 + run * R2) * PB + cp * VEC;
-        const int g1 = a1 + cp * VEC, g2 = a2 + run * R2;
+        c_src[k] = (m * W2 + run * R2) * PB + cp * CW;
+        const int g1 = a1 + cp * CW, g2 = a2 + run * R2;
         int rows = min(R2, n2 - g2);
         if (it >= NC_ITEMS || g1 >= n1 || rows < 0) rows = 0;
         c_rows[k] = rows;
@@ -293,35 +295,52 @@ k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
         }
         __syncthreads();
 
-        // ---- stage C: dim 2, SB[m][rows][chunk] -> subbands in global memory (16-byte streaming stores)
+        // ---- stage C: dim 2, SB[m][rows][cols] -> subbands in global memory (streaming stores).
+        // Sliding L-row register window per item (row r lives in slot r % L, the next row is loaded one
+        // output ahead), so the window costs the same registers for any run length R2.
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
             const int rows = c_rows[k];
             if (rows > 0) {
                 const T *col = SB + c_src[k];
-                T v[R2 + L - 1][VEC];
+                T w[L][CW];
 #pragma unroll
-                for (int j = 0; j < R2 + L - 1; ++j) ld_chunk<T, VEC>(col + j * PB, v[j]);
+                for (int j = 0; j < L; ++j) {
+                    if (CW == 1) w[j][0] = col[j * PB];
+                    else ld_chunk<T, CW>(col + j * PB, w[j]);
+                }
+                T *plo = c_lo[k], *phi = c_hi[k];
 #pragma unroll
                 for (int o = 0; o < R2; ++o) {
-                    T lo[VEC], hi[VEC];
+                    T lo[CW], hi[CW];
 #pragma unroll
-                    for (int e = 0; e < VEC; ++e) {
+                    for (int e = 0; e < CW; ++e) {
                         lo[e] = zero_of(T());
                         hi[e] = zero_of(T());
 #pragma unroll
                         for (int j = 0; j < L; ++j) {
-                            macp(lo[e], tp.lo[1][L - 1 - j], v[o + j][e]);
-                            macp(hi[e], tp.hi[1][L - 1 - j], v[o + j][e]);
+                            macp(lo[e], tp.lo[1][L - 1 - j], w[(o + j) % L][e]);
+                            macp(hi[e], tp.hi[1][L - 1 - j], w[(o + j) % L][e]);
                         }
                     }
-                    if (o < rows) {
-                        union { uint4 q; T t[VEC]; } a, b;
-#pragma unroll
-                        for (int e = 0; e < VEC; ++e) { a.t[e] = lo[e]; b.t[e] = hi[e]; }
-                        __stcs(reinterpret_cast<uint4 *>(c_lo[k] + (int64_t)o * n1), a.q);
-                        __stcs(reinterpret_cast<uint4 *>(c_hi[k] + (int64_t)o * n1), b.q);
+                    if (o + 1 < R2) {   // row o + L replaces row o (its last use was this output)
+                        if (CW == 1) w[o % L][0] = col[(o + L) * PB];
+                        else ld_chunk<T, CW>(col + (o + L) * PB, w[o % L]);
                     }
+                    if (o < rows) {
+                        if (CW == 1) {
+                            st_stream(plo, lo[0]);
+                            st_stream(phi, hi[0]);
+                        } else {
+                            union { uint4 q; T t[CW]; } a, b;
+#pragma unroll
+                            for (int e = 0; e < CW; ++e) { a.t[e] = lo[e]; b.t[e] = hi[e]; }
+                            __stcs(reinterpret_cast<uint4 *>(plo), a.q);
+                            __stcs(reinterpret_cast<uint4 *>(phi), b.q);
+                        }
+                    }
+                    plo += n1;
+                    phi += n1;
                 }
             }
             c_lo[k] += s3;
@@ -1058,7 +1077,7 @@ static int pick_zc(int n3, int tiles, int H, int ctas_per_wave)
     return best;
 }
 
-template <typename T, int L, int T2, int NT, int R2, int MINB>
+template <typename T, int L, int T2, int NT, int R2, int MINB, int CWSEL = 0>
 static int launch_dec3_v(nddwt_plan *p, const Dec3Params<T> &base, cudaStream_t s)
 {
     using G = Geo<T, L, T2>;
@@ -1069,7 +1088,7 @@ static int launch_dec3_v(nddwt_plan *p, const Dec3Params<T> &base, cudaStream_t 
     prm.zc = pick_zc(prm.n3, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB);
     prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
     prm.halo_below = (L / 2 - 1);
-    auto kern = k_dec3_fused<T, L, T2, NT, R2, MINB>;
+    auto kern = k_dec3_fused<T, L, T2, NT, R2, MINB, CWSEL>;
     static bool attr_done = false;
     if (!attr_done) {
         NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
@@ -1114,11 +1133,11 @@ static int launch_dec3(nddwt_plan *p, const void *a_in, const LevelIO &io, void 
     prm.s3 = p->dims[0] * p->dims[1];
     if constexpr (L == 8 && sizeof(T) == 8 && Elem<T>::cplx) {   // tuning variants (env NDDWT_VARIANT) for the headline case
         switch (tuning_variant() % 10) {
-            case 1: return launch_dec3_v<T, L, 16, 256, 4, 2>(p, prm, s);
-            case 2: return launch_dec3_v<T, L, 32, 512, 4, 1>(p, prm, s);
-            case 3: return launch_dec3_v<T, L, 16, 256, 4, 1>(p, prm, s);
-            case 4: return launch_dec3_v<T, L, 8, 256, 4, 2>(p, prm, s);
-            case 5: return launch_dec3_v<T, L, 16, 384, 4, 1>(p, prm, s);
+            case 1: return launch_dec3_v<T, L, 16, 256, 8, 2, 1>(p, prm, s);
+            case 2: return launch_dec3_v<T, L, 16, 256, 4, 2, 1>(p, prm, s);
+            case 3: return launch_dec3_v<T, L, 16, 256, 16, 2, 1>(p, prm, s);
+            case 4: return launch_dec3_v<T, L, 16, 256, 4, 2, 0>(p, prm, s);
+            case 5: return launch_dec3_v<T, L, 32, 512, 8, 1, 1>(p, prm, s);
             default: break;
         }
     }
