@@ -155,6 +155,16 @@ NDDWT_API int nddwt_rec_level_slab_stage1_part(nddwt_plan *plan, int level_index
 NDDWT_API int nddwt_rec_level_slab_stage2(nddwt_plan *plan, int level_index, const void *u_lo, const void *u_hi,
                                 const void *halo_lo, const void *halo_hi, void *a_out, void *stream);
 
+/* Scatter form of stage 2 (separable plans only): reads only the local u planes, writes the local
+ * partial result to a_out and the partial sums that belong to neighbouring slabs to over_lo
+ * (L/2-1 planes: global planes start-(L/2-1)..start-1) and over_hi (L/2 planes: end..end+L/2-1).
+ * The caller sends the overhangs to their owners, which add them with nddwt_accumulate.  Halves the
+ * synthesis halo traffic compared with exchanging u_lo and u_hi. */
+NDDWT_API int nddwt_rec_level_slab_stage2_scatter(nddwt_plan *plan, int level_index, const void *u_lo, const void *u_hi,
+                                        void *a_out, void *over_lo, void *over_hi, void *stream);
+/* dst[i] += src[i] for nelem elements of the plan's dtype (device pointers). */
+NDDWT_API int nddwt_accumulate(nddwt_plan *plan, void *dst, const void *src, int64_t nelem, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

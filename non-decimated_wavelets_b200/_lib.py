@@ -21,7 +21,7 @@ SYMBOLS = [
     "nddwt_plan_set_kernel_mode", "nddwt_plan_launch_count", "nddwt_plan_last_path",
     "nddwt_plan_profile", "nddwt_plan_kernel_time",
     "nddwt_dec", "nddwt_rec", "nddwt_dec_host", "nddwt_rec_host",
-    "nddwt_halo_planes", "nddwt_dec_level_slab", "nddwt_plan_is_separable", "nddwt_dec_level_slab_part", "nddwt_rec_level_slab_stage1_part", "nddwt_rec_level_slab_stage1", "nddwt_rec_level_slab_stage2",
+    "nddwt_halo_planes", "nddwt_dec_level_slab", "nddwt_plan_is_separable", "nddwt_dec_level_slab_part", "nddwt_rec_level_slab_stage1_part", "nddwt_rec_level_slab_stage2_scatter", "nddwt_accumulate", "nddwt_rec_level_slab_stage1", "nddwt_rec_level_slab_stage2",
 ]
 
 _lib = None
@@ -70,6 +70,8 @@ def lib():
     L.nddwt_plan_is_separable.argtypes = [vp]
     L.nddwt_dec_level_slab_part.argtypes = [vp, c.c_int, c.c_int, vp, vp, vp, c.POINTER(vp), vp]
     L.nddwt_rec_level_slab_stage1_part.argtypes = [vp, c.c_int, c.c_int, c.POINTER(vp), vp, vp, vp]
+    L.nddwt_rec_level_slab_stage2_scatter.argtypes = [vp, c.c_int, vp, vp, vp, vp, vp, vp]
+    L.nddwt_accumulate.argtypes = [vp, vp, vp, c.c_int64, vp]
     L.nddwt_rec_level_slab_stage1.argtypes = [vp, c.c_int, c.POINTER(vp), vp, vp, vp]
     L.nddwt_rec_level_slab_stage2.argtypes = [vp, c.c_int, vp, vp, vp, vp, vp, vp]
     _lib = L
@@ -177,6 +179,12 @@ class Plan:
     def rec_level_slab_stage1_part(self, level_index, part, in_ptrs, u_lo, u_hi, stream=0):
         arr = (ctypes.c_void_p * len(in_ptrs))(*in_ptrs)
         check(lib().nddwt_rec_level_slab_stage1_part(self.handle, level_index, part, arr, u_lo, u_hi, stream))
+
+    def rec_level_slab_stage2_scatter(self, level_index, u_lo, u_hi, a_out, over_lo, over_hi, stream=0):
+        check(lib().nddwt_rec_level_slab_stage2_scatter(self.handle, level_index, u_lo, u_hi, a_out, over_lo, over_hi, stream))
+
+    def accumulate(self, dst, src, nelem, stream=0):
+        check(lib().nddwt_accumulate(self.handle, dst, src, nelem, stream))
 
     def rec_level_slab_stage1(self, level_index, in_ptrs, u_lo, u_hi, stream=0):
         arr = (ctypes.c_void_p * len(in_ptrs))(*in_ptrs)

@@ -410,6 +410,26 @@ int nddwt_dec_level_slab(nddwt_plan *p, int level_index, const void *a_in, const
     return dec_level(p, p->dil[level_index - 1], a_in, io, out_bands, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int nddwt_rec_level_slab_stage2_scatter(nddwt_plan *p, int level_index, const void *u_lo, const void *u_hi,
+                                        void *a_out, void *over_lo, void *over_hi, void *stream)
+{
+    int rc = check_level(p, level_index);
+    if (rc) return rc;
+    if (!u_lo || !u_hi || !a_out || !over_lo || !over_hi) { set_error("null pointer"); return NDDWT_ERR_ARG; }
+    NDDWT_CUDA(cudaSetDevice(p->device));
+    rc = fused_rec_stage2_scatter(p, p->dil[level_index - 1], u_lo, u_hi, a_out, over_lo, over_hi,
+                                  reinterpret_cast<cudaStream_t>(stream));
+    if (rc > 0) { set_error("scatter-form synthesis needs a separable (fused 4-D) plan"); return NDDWT_ERR_ARG; }
+    return rc;
+}
+
+int nddwt_accumulate(nddwt_plan *p, void *dst, const void *src, int64_t nelem, void *stream)
+{
+    if (!p || !dst || !src || nelem < 0) { set_error("bad argument"); return NDDWT_ERR_ARG; }
+    NDDWT_CUDA(cudaSetDevice(p->device));
+    return accumulate_elems(p, dst, src, nelem, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int nddwt_plan_is_separable(const nddwt_plan *p) { return (p && fused_is_separable(p)) ? 1 : 0; }
 
 int nddwt_dec_level_slab_part(nddwt_plan *p, int level_index, int part, const void *a_in, const void *halo_lo,

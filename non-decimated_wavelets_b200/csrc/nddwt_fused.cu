@@ -18,6 +18,7 @@
 //     and streams the 8 subbands to global memory with fully coalesced st.global.cs.
 //   complex-single arithmetic is FFMA2 (fma.rn.f32x2) on (re, im) pairs with duplicated taps
 //   taken from the kernel-parameter constant bank.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <cuda.h>
@@ -1041,6 +1042,57 @@ k_rec_last(const T *__restrict__ u_lo, const T *__restrict__ u_hi, const T *__re
     }
 }
 
+// Scatter form of the last-dim synthesis for slabs: only the LOCAL u planes are read; the partial
+// sums that fall outside the slab (L/2-1 planes below, L/2 above) go to two overhang buffers which
+// the caller sends to the owning ranks (one array instead of the two u arrays of the gather form).
+template <typename T, int L>
+__global__ void __launch_bounds__(256)
+k_rec_last_scatter(const T *__restrict__ u_lo, const T *__restrict__ u_hi, T *__restrict__ out,
+                   T *__restrict__ over_lo, T *__restrict__ over_hi, int64_t nchunks, int n4, int64_t s4,
+                   const LastTaps<T, L> tp)
+{
+    constexpr int VEC = 16 / (int)sizeof(T), HB = L / 2, BELOW = L / 2 - 1;
+    const int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= nchunks) return;
+    const int64_t off = ci * VEC;
+    T acc[L][VEC];
+#pragma unroll
+    for (int j = 0; j < L; ++j)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[j][e] = zero_of(T());
+    // local coefficient plane zi = t - HB, t = HB .. HB + n4 - 1; then L-1 flush steps
+    const int nsteps = n4 + L - 1;
+    for (int tb = 0; tb < nsteps; tb += L) {
+#pragma unroll
+        for (int u = 0; u < L; ++u) {
+            const int tt = tb + u;
+            if (tt < nsteps) {
+                const int zi = tt;                       // 0 .. n4 + L - 2 (>= n4: flush with zeros)
+                T v0[VEC], v1[VEC];
+                if (zi < n4) {
+                    ld_chunk<T, VEC>(u_lo + (int64_t)zi * s4 + off, v0);
+                    ld_chunk<T, VEC>(u_hi + (int64_t)zi * s4 + off, v1);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) { v0[e] = zero_of(T()); v1[e] = zero_of(T()); }
+                }
+                // this step completes output plane m = zi - L/2 + 1
+                const int m = zi - HB + 1;
+                T *dst = (m < 0) ? over_lo + (int64_t)(m + BELOW) * s4
+                                 : (m >= n4 ? over_hi + (int64_t)(m - n4) * s4 : out + (int64_t)m * s4);
+                DispatchC<T, L, VEC, 0>::run(u, acc, v0, v1, tp.lo, tp.hi, dst + off, true);
+            }
+        }
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_accumulate(R *__restrict__ dst, const R *__restrict__ src, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] += src[i];
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -1302,6 +1354,22 @@ static int launch_rec3_bulk(nddwt_plan *p, const Rec3Params<T> &base, cudaStream
     return 0;
 }
 
+// tile-shape variants of the bulk synthesis kernel (NDDWT_VARIANT / 100 selects; 0 = default)
+template <typename T, int L>
+static int launch_rec3_bulk_any(nddwt_plan *p, const Rec3Params<T> &prm, cudaStream_t s)
+{
+    if constexpr (L == 8 && sizeof(T) == 8 && Elem<T>::cplx) {
+        switch (tuning_variant() / 100) {
+            case 1: return launch_rec3_bulk<T, L, 32, 640, 8, 1>(p, prm, s);
+            case 2: return launch_rec3_bulk<T, L, 8, 192, 8, 4>(p, prm, s);
+            case 3: return launch_rec3_bulk<T, L, 8, 160, 8, 4>(p, prm, s);
+            case 4: return launch_rec3_bulk<T, L, 8, 256, 8, 3>(p, prm, s);
+            default: break;
+        }
+    }
+    return launch_rec3_bulk<T, L, 16, 320, 8, 2>(p, prm, s);
+}
+
 template <typename T, int L>
 static int launch_rec3(nddwt_plan *p, const void *const *in_bands, void *a_out, cudaStream_t s)
 {
@@ -1328,7 +1396,7 @@ static int launch_rec3(nddwt_plan *p, const void *const *in_bands, void *a_out, 
             default: break;
         }
     }
-    if (prm.n1 >= GeoRB<T, L, 16>::W1S) return launch_rec3_bulk<T, L, 16, 320, 8, 2>(p, prm, s);
+    if (prm.n1 >= GeoRB<T, L, 16>::W1S) return launch_rec3_bulk_any<T, L>(p, prm, s);
     return launch_rec3_v<T, L, 16, 320, 8, 2>(p, prm, s);
 }
 
@@ -1419,6 +1487,31 @@ static int launch_rec_last(nddwt_plan *p, const T *u_lo, const T *u_hi, const Le
     return 0;
 }
 
+template <typename T, int L>
+static int launch_rec_last_scatter(nddwt_plan *p, const T *u_lo, const T *u_hi, T *out, T *over_lo, T *over_hi,
+                                   cudaStream_t s)
+{
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const int d = p->ndims - 1;
+    int64_t s4 = 1;
+    for (int i = 0; i < d; ++i) s4 *= p->dims[i];
+    const int64_t nchunks = s4 / VEC;
+    const int n4 = (int)p->dims[d];
+    const unsigned grid = (unsigned)((nchunks + 255) / 256);
+    {
+        LaunchTimer lt(p, KIND_REC_LAST, s);
+        k_rec_last_scatter<T, L><<<grid, 256, 0, s>>>(u_lo, u_hi, out, over_lo, over_hi, nchunks, n4, s4,
+                                                     make_last_taps<T, L>(p, true));
+    }
+    p->launches++;
+    NDDWT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int dispatch_rec_last_scatter(nddwt_plan *p, const void *u_lo, const void *u_hi, void *out, void *over_lo,
+                                     void *over_hi, cudaStream_t s);
+
 // part: 0 = whole level; 1 = dim-4 pass only (the one that needs the slab halos);
 //       2 = tile pass on the lo4 half (bands 0..7, incl. the approximation); 3 = tile pass on the hi4 half
 template <typename T, int L>
@@ -1477,7 +1570,7 @@ static int rec4_stage1(nddwt_plan *p, const void *const *in_bands, T *u_lo, T *u
     prm.s3 = p->dims[0] * p->dims[1];
     prm.s4 = prm.s3 * p->dims[2];
     prm.nhyp = (int)p->dims[3];
-    if (prm.n1 >= GeoRB<T, L, 16>::W1S) return launch_rec3_bulk<T, L, 16, 320, 8, 2>(p, prm, s);
+    if (prm.n1 >= GeoRB<T, L, 16>::W1S) return launch_rec3_bulk_any<T, L>(p, prm, s);
     return launch_rec3_v<T, L, 16, 320, 8, 2>(p, prm, s);
 }
 
@@ -1530,6 +1623,16 @@ static int dispatch_rec_last(nddwt_plan *p, const void *u_lo, const void *u_hi, 
                                                                  reinterpret_cast<T *>(a_out), s)));
 }
 
+template <typename T>
+static int dispatch_rec_last_scatter(nddwt_plan *p, const void *u_lo, const void *u_hi, void *out, void *over_lo,
+                                     void *over_hi, cudaStream_t s)
+{
+    NDDWT_L_SWITCH(p->L[p->ndims - 1],
+                   (launch_rec_last_scatter<T, LL>(p, reinterpret_cast<const T *>(u_lo), reinterpret_cast<const T *>(u_hi),
+                                                   reinterpret_cast<T *>(out), reinterpret_cast<T *>(over_lo),
+                                                   reinterpret_cast<T *>(over_hi), s)));
+}
+
 static bool fused_geometry_ok(const nddwt_plan *p)
 {
     if (p->ndims < 3) return false;
@@ -1553,6 +1656,29 @@ int fused_rec_stage1(nddwt_plan *p, int dil, const void *const *in_bands, void *
 {
     if (dil != 1 || !uniform_taps(p) || p->ndims != 4 || !fused_geometry_ok(p)) return 1;
     NDDWT_T_SWITCH(p, (dispatch_rec4_stage1<TT>(p, in_bands, u_lo, u_hi, s, part)));
+}
+
+int fused_rec_stage2_scatter(nddwt_plan *p, int dil, const void *u_lo, const void *u_hi, void *out, void *over_lo,
+                             void *over_hi, cudaStream_t s)
+{
+    if (dil != 1 || p->ndims != 4 || !fused_geometry_ok(p)) return 1;
+    NDDWT_T_SWITCH(p, (dispatch_rec_last_scatter<TT>(p, u_lo, u_hi, out, over_lo, over_hi, s)));
+}
+
+int accumulate_elems(nddwt_plan *p, void *dst, const void *src, int64_t nelem, cudaStream_t s)
+{
+    // element type is irrelevant for an elementwise add: count real scalars
+    const bool dbl = (p->dtype == NDDWT_F64 || p->dtype == NDDWT_C128);
+    const int64_t n = nelem * (int64_t)(p->esize / (dbl ? 8 : 4));
+    const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    {
+        LaunchTimer lt(p, KIND_REC_LAST, s);
+        if (dbl) k_accumulate<double><<<grid, 256, 0, s>>>(reinterpret_cast<double *>(dst), reinterpret_cast<const double *>(src), n);
+        else k_accumulate<float><<<grid, 256, 0, s>>>(reinterpret_cast<float *>(dst), reinterpret_cast<const float *>(src), n);
+    }
+    p->launches++;
+    NDDWT_CUDA(cudaGetLastError());
+    return 0;
 }
 
 bool fused_is_separable(const nddwt_plan *p)

@@ -85,6 +85,9 @@ int fused_rec_stage2(nddwt_plan *p, int dil, const void *u_lo, const void *u_hi,
                      cudaStream_t s);
 
 bool fused_is_separable(const nddwt_plan *p);
+int fused_rec_stage2_scatter(nddwt_plan *p, int dil, const void *u_lo, const void *u_hi, void *out, void *over_lo,
+                             void *over_hi, cudaStream_t s);
+int accumulate_elems(nddwt_plan *p, void *dst, const void *src, int64_t nelem, cudaStream_t s);
 int ensure_scratch(nddwt_plan *p);
 
 // kernel kinds for nddwt_plan_kernel_time

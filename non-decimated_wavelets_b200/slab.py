@@ -86,6 +86,8 @@ class HaloExchanger:
                 for k, (o, idx, cnt, _) in enumerate(runs):
                     if o == rank:
                         self.send.append((peer, idx, cnt, which, k))
+        # planes other ranks need from this one (= planes received by reverse_exchange)
+        self.stage_planes = sum(cnt for peer, _, cnt, _, _ in self.send if peer != rank)
 
     def exchange(self, local, halo_lo, halo_hi):
         """local: [n_local, ...] contiguous; halo_lo: [below, ...]; halo_hi: [above, ...] (filled in place).
@@ -109,6 +111,31 @@ class HaloExchanger:
             dst[off:off + cnt].copy_(local[idx:idx + cnt])
         for r in reqs:
             r.wait()
+
+
+def reverse_exchange(xch, over_lo, over_hi, stage):
+    """Adjoint of HaloExchanger.exchange: over_lo / over_hi hold partial sums this rank computed for
+    planes owned by other ranks (same plane sets as the halos of `xch`); they are sent to the owners.
+    What other ranks computed for MY planes arrives in `stage` ([total, ...]).  Returns the list of
+    (local_first_plane, count, stage_offset) runs the caller has to add into its result."""
+    ops, adds, self_adds = [], [], []
+    off = 0
+    for peer, idx, cnt, which, k in xch.send:            # forward mode: I send planes idx.. to `peer`
+        if peer == xch.rank:
+            continue
+        ops.append(dist.P2POp(dist.irecv, stage[off:off + cnt], peer, group=xch.group, tag=which * 64 + k))
+        adds.append((idx, cnt, off))
+        off += cnt
+    for which, runs, src in ((0, xch.recv_lo, over_lo), (1, xch.recv_hi, over_hi)):
+        for k, (o, idx, cnt, o_off) in enumerate(runs):  # forward mode: I receive these planes from `o`
+            if o == xch.rank:
+                self_adds.append((idx, cnt, src, o_off))
+            else:
+                ops.append(dist.P2POp(dist.isend, src[o_off:o_off + cnt], o, group=xch.group, tag=which * 64 + k))
+    reqs = dist.batch_isend_irecv(ops) if ops else []
+    for r in reqs:
+        r.wait()
+    return adds, self_adds
 
 
 class CudaSlabEngine:
@@ -139,6 +166,13 @@ class CudaSlabEngine:
     def dec_level_part(self, level, part, a_in, halo_lo, halo_hi, out_bands):
         self.plan.dec_level_slab_part(level, part, a_in.data_ptr(), halo_lo.data_ptr(), halo_hi.data_ptr(),
                                       [t.data_ptr() for t in out_bands], self._stream())
+
+    def rec_stage2_scatter(self, level, u_lo, u_hi, a_out, over_lo, over_hi):
+        self.plan.rec_level_slab_stage2_scatter(level, u_lo.data_ptr(), u_hi.data_ptr(), a_out.data_ptr(),
+                                                over_lo.data_ptr(), over_hi.data_ptr(), self._stream())
+
+    def accumulate(self, dst, src):
+        self.plan.accumulate(dst.data_ptr(), src.data_ptr(), dst.numel(), self._stream())
 
     def rec_stage1_part(self, level, part, in_bands, u_lo, u_hi):
         self.plan.rec_level_slab_stage1_part(level, part, [t.data_ptr() for t in in_bands], u_lo.data_ptr(),
@@ -184,6 +218,10 @@ class SlabTransform:
             self.comm_stream = torch.cuda.Stream(device=device, priority=-1)
             self.u_hi2 = [self.u[1], torch.empty(self.local_shape, dtype=dtype, device=device)]
             self.h_rec2 = [self.h_rec, (mk(self.L // 2, 2), mk(self.L // 2 - 1, 2))]
+            # scatter-form synthesis exchange: overhang partial sums (same plane sets as the analysis halos)
+            self.scatter = os.environ.get("NDDWT_SLAB_SCATTER", "1") != "0"
+            self.over = (mk(lo_d), mk(hi_d))
+            self.stage = mk(self.x_dec.stage_planes)
 
     def num_bands(self, level):
         nd = 1 << self.d
@@ -215,7 +253,45 @@ class SlabTransform:
             a_in = bands[0]
         return out
 
+    def _rec_overlapped_scatter(self, coeffs, out):
+        """Synthesis with the scatter-form exchange: per level one array of overhang partial sums moves
+        (L-1 planes) instead of the halos of u_lo and u_hi; the detail-only half of the NEXT level's
+        stage 1 runs while they are in flight."""
+        nd = 1 << self.d
+        nb = coeffs.shape[0]
+        level = 1 + (nb - nd) // (nd - 1)
+        cur = torch.cuda.current_stream(coeffs.device)
+        comm = self.comm_stream
+        u_lo = self.u[0]
+        over_lo, over_hi = self.over
+
+        def bands_of(j, a):
+            start = (nd - 1) * (level - j)
+            return [a] + [coeffs[start + b] for b in range(1, nd)]
+
+        a = coeffs[0]
+        self.engine.rec_stage1_part(level, 2, bands_of(level, a), u_lo, self.u_hi2[level & 1])
+        for j in range(level, 0, -1):
+            k = j & 1
+            dst = out if j == 1 else self.approx[j & 1]
+            self.engine.rec_stage1_part(j, 1, bands_of(j, a), u_lo, self.u_hi2[k])
+            self.engine.rec_stage2_scatter(j, u_lo, self.u_hi2[k], dst, over_lo, over_hi)
+            comm.wait_stream(cur)
+            with torch.cuda.stream(comm):
+                adds, self_adds = reverse_exchange(self.x_dec, over_lo, over_hi, self.stage)
+            if j > 1:   # detail half of the next level: independent of dst, overlaps with the exchange
+                self.engine.rec_stage1_part(j - 1, 2, bands_of(j - 1, coeffs[0]), u_lo, self.u_hi2[(j - 1) & 1])
+            cur.wait_stream(comm)
+            for idx, cnt, off in adds:
+                self.engine.accumulate(dst[idx:idx + cnt], self.stage[off:off + cnt])
+            for idx, cnt, src, o_off in self_adds:
+                self.engine.accumulate(dst[idx:idx + cnt], src[o_off:o_off + cnt])
+            a = dst
+        return out
+
     def _rec_overlapped(self, coeffs, out):
+        if getattr(self, "scatter", False):
+            return self._rec_overlapped_scatter(coeffs, out)
         nd = 1 << self.d
         nb = coeffs.shape[0]
         level = 1 + (nb - nd) // (nd - 1)

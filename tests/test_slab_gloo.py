@@ -140,3 +140,50 @@ def test_slab_transform_world(world, sizes, wnames, level, l2):
     res = [q.get(timeout=5) for _ in range(world)]
     for rank, e_dec, e_rec in res:
         assert e_dec < 1e-12 and e_rec < 1e-12, (rank, e_dec, e_rec)
+
+
+def _adj_worker(rank, world, port, n_last, below, above, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        parts = slab.slab_partition(n_last, world)
+        s, c = parts[rank]
+        g = torch.Generator().manual_seed(100 + rank)
+        x = torch.randn((c, 5), generator=g, dtype=torch.float64)
+        ylo = torch.randn((max(below, 1), 5), generator=g, dtype=torch.float64)
+        yhi = torch.randn((max(above, 1), 5), generator=g, dtype=torch.float64)
+        xch = slab.HaloExchanger(n_last, world, rank, below, above)
+        hlo, hhi = torch.zeros_like(ylo), torch.zeros_like(yhi)
+        xch.exchange(x, hlo, hhi)                                  # forward: halos of x
+        lhs = (hlo[:below] * ylo[:below]).sum() + (hhi[:above] * yhi[:above]).sum()
+        stage = torch.zeros((max(xch.stage_planes, 1), 5), dtype=torch.float64)
+        adds, self_adds = slab.reverse_exchange(xch, ylo, yhi, stage)   # adjoint: scatter-add of y
+        z = torch.zeros_like(x)
+        for idx, cnt, off in adds:
+            z[idx:idx + cnt] += stage[off:off + cnt]
+        for idx, cnt, src, o_off in self_adds:
+            z[idx:idx + cnt] += src[o_off:o_off + cnt]
+        rhs = (x * z).sum()
+        both = torch.stack([lhs, rhs])
+        dist.all_reduce(both)
+        q.put((rank, float(both[0]), float(both[1])))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_last,below,above", [(2, 16, 3, 4), (3, 7, 3, 4), (2, 8, 0, 1)])
+def test_reverse_exchange_is_adjoint_of_exchange(world, n_last, below, above):
+    """<exchange(x), y> == <x, reverse_exchange(y)> summed over ranks (scatter-form synthesis exchange)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_adj_worker, args=(r, world, port, n_last, below, above, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    for _ in range(world):
+        rank, lhs, rhs = q.get(timeout=5)
+        assert abs(lhs - rhs) <= 1e-10 * max(1.0, abs(lhs)), (rank, lhs, rhs)
