@@ -47,9 +47,17 @@ def run_multi(args, wl_name, wl):
     y = torch.empty((nb,) + tr.local_shape, dtype=tdt, device=dev)
     xr = torch.empty_like(x)
 
-    def step():
+    split = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+
+    def step(timed=False):
+        if timed:
+            split[0].record()
         tr.dec(x, level, out=y)
+        if timed:
+            split[1].record()
         tr.rec(y, out=xr)
+        if timed:
+            split[2].record()
 
     for _ in range(max(3, args.warmup)):
         step()
@@ -60,6 +68,11 @@ def run_multi(args, wl_name, wl):
     dist.all_reduce(both)
     pr_err = float(torch.sqrt(both[0] / both[1]))
 
+    dist.barrier()
+    torch.cuda.synchronize()
+    step(timed=True)
+    torch.cuda.synchronize()
+    dec_ms, rec_ms = split[0].elapsed_time(split[1]), split[1].elapsed_time(split[2])
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -85,7 +98,7 @@ def run_multi(args, wl_name, wl):
     pair_bytes = 2 * (1 + nb) * nvox * esize
     pair_gbs = pair_bytes / (ms_per_step * 1e-3) / 1e9
     plane_bytes = int(np.prod(sizes[:-1])) * esize
-    halo_bytes = level * (L - 1) * plane_bytes * 3     # per rank per pair: analysis 1 band, synthesis 2 arrays
+    halo_bytes = level * (L - 1) * plane_bytes * (2 if getattr(tr, 'scatter', False) else 3)   # per rank per pair
     if rank == 0:
         line = {
             "metric": "dec+rec Mvoxels/s", "value": value, "unit": "Mvoxels/s", "n_gpus": world,
@@ -96,7 +109,9 @@ def run_multi(args, wl_name, wl):
                        "elem": dtype, "parallelism": "slab%d (last dim, %s planes/GPU), NCCL halo exchange per level"
                        % (world, "/".join(str(c) for _, c in parts)),
                        "l2": "per-GPU working set %.1f GB >> L2, no flush" % ((1 + nb) * nvox * esize / world / 1e9),
-                       "pr_rel_err": pr_err, "halo_bytes_per_rank_per_step": halo_bytes},
+                       "pr_rel_err": pr_err, "halo_bytes_per_rank_per_step": halo_bytes,
+                       "dec_ms_rank0": dec_ms, "rec_ms_rank0": rec_ms, "overlap": bool(tr.overlap),
+                       "scatter_exchange": bool(getattr(tr, "scatter", False))},
             "roofline": {"bound": "hbm", "achieved": pair_gbs / world, "peak": peak, "unit": "GB/s",
                          "frac": pair_gbs / world / peak, "traffic": None,
                          "kernel": "whole dec+rec pair per GPU (compulsory bytes 2(1+nb)Ne / P)",

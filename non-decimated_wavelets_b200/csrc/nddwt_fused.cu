@@ -342,6 +342,7 @@ k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
                     }
                     plo += n1;
                     phi += n1;
+                    asm volatile("" ::: "memory");   // keep the window loads of later rows from being hoisted (register pressure)
                 }
             }
             c_lo[k] += s3;

@@ -100,3 +100,86 @@ def test_emulated_ranks_match_oracle(sizes, wname, level, world, l2):
 def test_slab_fused_path_is_taken_for_4d():
     _, _, _, fused = _emulate((32, 24, 16, 16), "db4", 1, 4, 0)
     assert all(f == 1 for f in fused)
+
+
+def test_partwise_and_scatter_entry_points_match_oracle():
+    """The part-wise analysis calls and the scatter-form synthesis (overhang partial sums + accumulate)
+    used by the overlapped multi-GPU schedule, emulated for 4 ranks on one GPU."""
+    import torch
+    sizes, wname, level, world, l2 = (32, 24, 16, 16), "db4", 2, 4, 0
+    d = len(sizes)
+    wn = [wname] * d
+    L = 8
+    below, above = L // 2 - 1, L // 2
+    x = orc.synth(sizes, np.complex64, 5)
+    xbase = nd.to_device(x).permute(*reversed(range(d))).contiguous()
+    parts = slab.slab_partition(sizes[-1], world)
+    n = sizes[-1]
+    nd_b = 1 << d
+    nb = nd_b + (nd_b - 1) * (level - 1)
+    engines = [slab.CudaSlabEngine(tuple(sizes[:-1]) + (c,), n, wn, _lib.NDDWT_C64, l2, 0) for (s, c) in parts]
+    assert all(e.separable for e in engines)
+    plane = tuple(reversed(sizes[:-1]))
+
+    def halos(full, s, c):
+        lo = full.index_select(0, torch.tensor([(s - below + i) % n for i in range(below)], device="cuda"))
+        hi = full.index_select(0, torch.tensor([(s + c + i) % n for i in range(above)], device="cuda"))
+        return lo.contiguous(), hi.contiguous()
+
+    coeffs = [torch.empty((nb, c) + plane, dtype=torch.complex64, device="cuda") for (s, c) in parts]
+    a_full = xbase
+    for j in range(1, level + 1):
+        start = (nd_b - 1) * (level - j)
+        new_a = []
+        for r, (s, c) in enumerate(parts):
+            lo, hi = halos(a_full, s, c)
+            a0 = coeffs[r][0] if j == level else torch.empty_like(coeffs[r][0])
+            bands = [a0] + [coeffs[r][start + b] for b in range(1, nd_b)]
+            a_in = a_full[s:s + c].contiguous()
+            for part in (1, 2, 3):
+                engines[r].dec_level_part(j, part, a_in, lo, hi, bands)
+            new_a.append(a0)
+        a_full = torch.cat(new_a, dim=0)
+    y = torch.cat(coeffs, dim=1)
+    yo = orc.dec_direct(x.astype(np.complex128), wn, level, bool(l2))
+    assert orc.rel_l2(nd.to_host(y.permute(*reversed(range(d + 1)))), yo) <= 1e-5
+
+    a_full = y[0]
+    for j in range(level, 0, -1):
+        start = (nd_b - 1) * (level - j)
+        out_full = torch.zeros((n,) + plane, dtype=torch.complex64, device="cuda")
+        for r, (s, c) in enumerate(parts):
+            bands = [a_full[s:s + c].contiguous()] + [coeffs[r][start + b] for b in range(1, nd_b)]
+            u_lo, u_hi = torch.empty_like(bands[0]), torch.empty_like(bands[0])
+            engines[r].rec_stage1_part(j, 2, bands, u_lo, u_hi)      # detail half first, as the schedule does
+            engines[r].rec_stage1_part(j, 1, bands, u_lo, u_hi)
+            loc = torch.empty_like(bands[0])
+            over_lo = torch.empty((below,) + plane, dtype=torch.complex64, device="cuda")
+            over_hi = torch.empty((above,) + plane, dtype=torch.complex64, device="cuda")
+            engines[r].rec_stage2_scatter(j, u_lo, u_hi, loc, over_lo, over_hi)
+            # what NCCL + nddwt_accumulate do between ranks, here by index on the assembled array
+            full_slot = out_full[s:s + c]
+            engines[r].accumulate(full_slot, loc)
+            for i in range(below):
+                engines[r].accumulate(out_full[(s - below + i) % n], over_lo[i])
+            for i in range(above):
+                engines[r].accumulate(out_full[(s + c + i) % n], over_hi[i])
+        a_full = out_full
+    torch.cuda.synchronize()
+    assert orc.rel_l2(nd.to_host(a_full.permute(*reversed(range(d)))), x) <= 1e-5
+
+
+def test_kernel_profile_api():
+    import torch
+    o = nd.nd_dwt_3D("db4", [64, 48, 40], "precision", "single", "compute", "gpu")
+    x = nd.to_device(orc.synth((64, 48, 40), np.complex64, 1))
+    y = o.dec(x, 2)
+    plan = o._plan(True, 0)
+    plan.profile(True)
+    y = o.dec(x, 2)
+    o.rec(y)
+    plan.profile(False)
+    ms_dec, n_dec = plan.kernel_time(0)
+    ms_rec, n_rec = plan.kernel_time(1)
+    assert n_dec == 2 and n_rec == 2 and ms_dec > 0 and ms_rec > 0
+    assert plan.kernel_time(0) == (0.0, 0)          # reading clears
