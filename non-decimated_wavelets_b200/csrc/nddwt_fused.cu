@@ -372,6 +372,7 @@ struct Rec3Params {
     int tiles1, tiles2, zc, nchunks;
     int prefetch;       // 0 none, 1 prefetch.global.L1 of the next plane's footprint, 2 prefetch.global.L2
     int cl1, cl2;       // thread-block cluster shape in tiles (cl1 x cl2 CTAs, 1 x 1 = no cluster)
+    int hint;           // 1: stage the subband tiles with an L2 evict_last policy
 };
 
 template <typename T, int L, int T2>
@@ -649,6 +650,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -681,6 +696,15 @@ struct TmaMaps {
     CUtensorMap m[16];      // one 3-D map (n1, n2, planes) per subband array; box = (W1S, W2, 1)
 };
 
+__device__ __forceinline__ void tma_load_3d_hint(void *dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar,
+                                                 uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar)
 {
     asm volatile(
@@ -738,6 +762,7 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp, const __grid_consta
 
     // interior tiles (no periodic wrap inside the haloed box) are staged with ONE tensor TMA per
     // subband, issued by a single thread; edge tiles fall back to per-row bulk copies
+    const uint64_t pol = p.hint ? l2_policy_evict_last() : 0;
     const bool use_tma = p.prefetch == 3 && (a1 - HBAL >= 0) && (a1 - HBAL + W1S <= n1) && (a2 - HB >= 0) &&
                          (a2 - HB + W2 <= n2);
     // ---- hoisted per-thread constants ----
@@ -823,7 +848,7 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp, const __grid_consta
         if (tid == 0) {
             const int zp = bhyp * n3 + wrapi(z0 - HB, n3);
 #pragma unroll
-            for (int b = 0; b < 8; ++b) tma_load_3d(RAW + b * BP, &maps.m[8 * bsel + b], a1 - HBAL, a2 - HB, zp, bar);
+            for (int b = 0; b < 8; ++b) { if (p.hint) tma_load_3d_hint(RAW + b * BP, &maps.m[8 * bsel + b], a1 - HBAL, a2 - HB, zp, bar, pol); else tma_load_3d(RAW + b * BP, &maps.m[8 * bsel + b], a1 - HBAL, a2 - HB, zp, bar); }
         }
     } else {
         const int64_t zoff = (int64_t)wrapi(z0 - HB, n3) * s3;
@@ -833,8 +858,13 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp, const __grid_consta
                 const T *src = r_src[k] + zoff;
                 T *dst = RAW + r_dst[k];
                 const int len0 = r_len0[k];
-                bulk_g2s(dst, src + r_col1[k], (uint32_t)(len0 * sizeof(T)), bar);
-                if (len0 < W1S) bulk_g2s(dst + len0, src, (uint32_t)((W1S - len0) * sizeof(T)), bar);
+                if (p.hint) {
+                    bulk_g2s_hint(dst, src + r_col1[k], (uint32_t)(len0 * sizeof(T)), bar, pol);
+                    if (len0 < W1S) bulk_g2s_hint(dst + len0, src, (uint32_t)((W1S - len0) * sizeof(T)), bar, pol);
+                } else {
+                    bulk_g2s(dst, src + r_col1[k], (uint32_t)(len0 * sizeof(T)), bar);
+                    if (len0 < W1S) bulk_g2s(dst + len0, src, (uint32_t)((W1S - len0) * sizeof(T)), bar);
+                }
             }
         }
     }
@@ -880,7 +910,7 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp, const __grid_consta
                     const int zp = bhyp * n3 + wrapi(z0 - HB + t + 1, n3);
 #pragma unroll
                     for (int b = 0; b < 8; ++b)
-                        tma_load_3d(RAW + b * BP, &maps.m[8 * bsel + b], a1 - HBAL, a2 - HB, zp, bar);
+                        { if (p.hint) tma_load_3d_hint(RAW + b * BP, &maps.m[8 * bsel + b], a1 - HBAL, a2 - HB, zp, bar, pol); else tma_load_3d(RAW + b * BP, &maps.m[8 * bsel + b], a1 - HBAL, a2 - HB, zp, bar); }
                 }
             } else {
                 const int64_t zoff = (int64_t)wrapi(z0 - HB + t + 1, n3) * s3;
@@ -890,8 +920,13 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp, const __grid_consta
                         const T *src = r_src[k] + zoff;
                         T *dst = RAW + r_dst[k];
                         const int len0 = r_len0[k];
-                        bulk_g2s(dst, src + r_col1[k], (uint32_t)(len0 * sizeof(T)), bar);
-                        if (len0 < W1S) bulk_g2s(dst + len0, src, (uint32_t)((W1S - len0) * sizeof(T)), bar);
+                        if (p.hint) {
+                            bulk_g2s_hint(dst, src + r_col1[k], (uint32_t)(len0 * sizeof(T)), bar, pol);
+                            if (len0 < W1S) bulk_g2s_hint(dst + len0, src, (uint32_t)((W1S - len0) * sizeof(T)), bar, pol);
+                        } else {
+                            bulk_g2s(dst, src + r_col1[k], (uint32_t)(len0 * sizeof(T)), bar);
+                            if (len0 < W1S) bulk_g2s(dst + len0, src, (uint32_t)((W1S - len0) * sizeof(T)), bar);
+                        }
                     }
                 }
             }
@@ -1278,6 +1313,14 @@ static EncodeTiledFn encode_fn()
     return fn;
 }
 
+static CUtensorMapL2promotion l2_promotion()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("NDDWT_L2PROMO"); v = e ? atoi(e) : 0; }
+    return v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                               : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+}
+
 // 3-D map over one subband array of 8-byte elements: (n1, n2, planes), box (bw, bh, 1)
 static bool encode_band_map(CUtensorMap *map, const void *base, int n1, int n2, int64_t planes, int bw, int bh)
 {
@@ -1288,7 +1331,7 @@ static bool encode_band_map(CUtensorMap *map, const void *base, int n1, int n2, 
     const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void *>(base), gdim, gstr, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2_promotion(),
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -1304,6 +1347,11 @@ static int launch_rec3_bulk(nddwt_plan *p, const Rec3Params<T> &base, cudaStream
     prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
     prm.prefetch = 0;
     prm.cl1 = prm.cl2 = 1;
+    {
+        static int hint = -1;
+        if (hint < 0) { const char *e = getenv("NDDWT_L2HINT"); hint = e ? atoi(e) : 0; }
+        prm.hint = hint;
+    }
     TmaMaps maps;
     memset(&maps, 0, sizeof maps);
     {
