@@ -392,7 +392,7 @@ struct GeoR {
 template <typename T, int L, int VEC, int U>
 __device__ __forceinline__ void rec_stage_c(T (&acc)[L][VEC], const T (&v0)[VEC], const T (&v1)[VEC],
                                             const typename TapOf<T>::type *lo, const typename TapOf<T>::type *hi,
-                                            T *dst, bool store)
+                                            T *dst, bool store, bool rmw = false)
 {
     // coefficient plane t (phase U = t mod L) feeds output planes n = z0 + t - k, slot (U - k) mod L
 #pragma unroll
@@ -408,6 +408,12 @@ __device__ __forceinline__ void rec_stage_c(T (&acc)[L][VEC], const T (&v0)[VEC]
         union { uint4 q; T t[VEC]; } a;
 #pragma unroll
         for (int e = 0; e < VEC; ++e) a.t[e] = acc[(U + 1) % L][e];
+        if (rmw) {   // periodic closure: add the partial sum this thread stored at the start of the march
+            union { uint4 q; T t[VEC]; } b;
+            b.q = __ldcg(reinterpret_cast<const uint4 *>(dst));   // L2-coherent load of this thread's own earlier store
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) a.t[e] = add(a.t[e], b.t[e]);
+        }
         __stcs(reinterpret_cast<uint4 *>(dst), a.q);
     }
 #pragma unroll
@@ -418,17 +424,17 @@ template <typename T, int L, int VEC, int U>
 struct DispatchC {
     __device__ __forceinline__ static void run(int u, T (&acc)[L][VEC], const T (&v0)[VEC], const T (&v1)[VEC],
                                                const typename TapOf<T>::type *lo, const typename TapOf<T>::type *hi,
-                                               T *dst, bool store)
+                                               T *dst, bool store, bool rmw = false)
     {
-        if (u == U) rec_stage_c<T, L, VEC, U>(acc, v0, v1, lo, hi, dst, store);
-        else DispatchC<T, L, VEC, U + 1>::run(u, acc, v0, v1, lo, hi, dst, store);
+        if (u == U) rec_stage_c<T, L, VEC, U>(acc, v0, v1, lo, hi, dst, store, rmw);
+        else DispatchC<T, L, VEC, U + 1>::run(u, acc, v0, v1, lo, hi, dst, store, rmw);
     }
 };
 template <typename T, int L, int VEC>
 struct DispatchC<T, L, VEC, L> {
     __device__ __forceinline__ static void run(int, T (&)[L][VEC], const T (&)[VEC], const T (&)[VEC],
                                                const typename TapOf<T>::type *, const typename TapOf<T>::type *, T *,
-                                               bool) {}
+                                               bool, bool = false) {}
 };
 
 template <typename T, int L, int T2, int NT, int R2, int MINB>
@@ -841,7 +847,11 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp, const __grid_consta
     __syncthreads();
     // the expect_tx of thread 0 must precede every complete_tx of the same phase: warp 0 issues it
     // first inside issue_plane; the other warps' copies may only start after it -> barrier
-    const int nsteps = (z1 - z0) + L - 1;
+    // single chunk = the whole periodic dimension: every coefficient plane is staged exactly once; the
+    // L-1 output planes that wrap around get the partial sum of the first steps stored early and the
+    // rest added by L-1 flush steps at the end (periodic closure) instead of re-reading L-1 planes
+    const bool closed = (p.nchunks == 1);
+    const int nsteps = closed ? (z1 - z0) : (z1 - z0) + L - 1;
     if (tid < 32) { if (tid == 0) mbar_expect_tx(bar, PLANE_BYTES); }
     __syncthreads();
     if (use_tma) {
@@ -958,19 +968,36 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp, const __grid_consta
         __syncthreads();
 
         // ---- stage RC: dim 3 scatter ring
-        const bool store = (t >= L - 1);
+        const bool store = closed || (t >= L - 1);
+        const int64_t wrap_off = (closed && t < L - 1) ? (int64_t)n3 * s3 : 0;   // early partials of the wrapped planes
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
             if (tid + k * NT < NC_ITEMS) {
                 T v0[VEC], v1[VEC];
                 ld_chunk<T, VEC>(SV + c_src[k], v0);
                 ld_chunk<T, VEC>(SV + c_src[k] + T2 * PV, v1);
-                DispatchC<T, L, VEC, 0>::run(u, acc[k], v0, v1, tp.lo[2], tp.hi[2], c_out[k], store && c_ok[k]);
+                DispatchC<T, L, VEC, 0>::run(u, acc[k], v0, v1, tp.lo[2], tp.hi[2], c_out[k] + wrap_off,
+                                             store && c_ok[k]);
                 c_out[k] += s3;
             }
         }
         u = (u + 1 == L) ? 0 : u + 1;
         if (csz > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+    }
+    if (closed) {   // flush: planes n3-L+1 .. n3-1 = early partial (already in memory) + what is left in the ring
+        for (int f = 0; f < L - 1; ++f) {
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                if (tid + k * NT < NC_ITEMS) {
+                    T v0[VEC], v1[VEC];
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) { v0[e] = zero_of(T()); v1[e] = zero_of(T()); }
+                    DispatchC<T, L, VEC, 0>::run(u, acc[k], v0, v1, tp.lo[2], tp.hi[2], c_out[k], c_ok[k], true);
+                    c_out[k] += s3;
+                }
+            }
+            u = (u + 1 == L) ? 0 : u + 1;
+        }
     }
 }
 
@@ -1246,7 +1273,7 @@ static int dispatch_dec3(nddwt_plan *p, int L, const void *a_in, const LevelIO &
 }
 
 
-static int pick_zc_rec(int n3, int units_per_plane_chunk, int H, int slots)
+static int pick_zc_rec(int n3, int units_per_plane_chunk, int H, int slots, bool closure = false)
 {
     // synthesis pays the full pipeline for the L-1 warm-up planes of every chunk: minimise
     // ceil(units / slots) * (zc + H)
@@ -1256,7 +1283,7 @@ static int pick_zc_rec(int n3, int units_per_plane_chunk, int H, int slots)
         const int zc = (n3 + nch - 1) / nch;
         if (zc < 4 && nch > 1) break;
         const int64_t units = (int64_t)units_per_plane_chunk * ((n3 + zc - 1) / zc);
-        const double cost = (double)((units + slots - 1) / slots) * (zc + H);
+        const double cost = (double)((units + slots - 1) / slots) * (zc + ((nch == 1 && closure) ? 0 : H));
         if (cost < best_cost - 1e-9) { best_cost = cost; best = zc; }
     }
     return best;
@@ -1343,7 +1370,7 @@ static int launch_rec3_bulk(nddwt_plan *p, const Rec3Params<T> &base, cudaStream
     prm.tiles1 = (prm.n1 + G::T1 - 1) / G::T1;
     prm.tiles2 = (prm.n2 + T2 - 1) / T2;
     const int batches = prm.nhyp * (prm.out[1] ? 2 : 1);
-    prm.zc = pick_zc_rec(prm.n3, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB);
+    prm.zc = pick_zc_rec(prm.n3, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB, true);
     prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
     prm.prefetch = 0;
     prm.cl1 = prm.cl2 = 1;
