@@ -117,7 +117,10 @@ def run_multi(args, wl_name, wl):
                          "kernel": "whole dec+rec pair per GPU (compulsory bytes 2(1+nb)Ne / P)",
                          "peak_source": peak_src},
             "cpu_baseline": None,
-            "e2e": None, "gpu_launches": int(launches) * world, "clocks": clocks,
+            "e2e": {"value": None, "unit": "Mvoxels/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                    "unavailable": "the cfg4 coefficient stack is 197.6 GB: host buffers for it do not fit the box's "
+                                   "196 GB of RAM at any N; the host-buffer path is measured at N=1 (cfg5)"},
+            "gpu_launches": int(launches) * world, "clocks": clocks,
         }
         print(json.dumps(line))
     dist.destroy_process_group()

@@ -54,6 +54,8 @@ static int dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io
     if (p->kernel_mode == 0) {
         int rc = fused_dec_level(p, dil, a_in, io, out_bands, s);
         if (rc <= 0) { p->last_path = 1; return rc; }
+        rc = fused2d_dec_level(p, dil, a_in, io, out_bands, s);
+        if (rc <= 0) { p->last_path = 1; return rc; }
     }
     p->last_path = 0;
     return generic_dec_level(p, dil, a_in, io, out_bands, s);
@@ -63,6 +65,8 @@ static int rec_level(nddwt_plan *p, int dil, const void *const *in_bands, void *
 {
     if (p->kernel_mode == 0) {
         int rc = fused_rec_level(p, dil, in_bands, a_out, s);
+        if (rc <= 0) { p->last_path = 1; return rc; }
+        rc = fused2d_rec_level(p, dil, in_bands, a_out, s);
         if (rc <= 0) { p->last_path = 1; return rc; }
     }
     p->last_path = 0;

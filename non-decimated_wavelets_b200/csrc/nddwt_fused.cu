@@ -1248,11 +1248,12 @@ static int launch_dec3(nddwt_plan *p, const void *a_in, const LevelIO &io, void 
     prm.s3 = p->dims[0] * p->dims[1];
     if constexpr (L == 8 && sizeof(T) == 8 && Elem<T>::cplx) {   // tuning variants (env NDDWT_VARIANT) for the headline case
         switch (tuning_variant() % 10) {
-            case 1: return launch_dec3_v<T, L, 16, 256, 8, 2, 1>(p, prm, s);
-            case 2: return launch_dec3_v<T, L, 16, 256, 4, 2, 1>(p, prm, s);
-            case 3: return launch_dec3_v<T, L, 16, 256, 16, 2, 1>(p, prm, s);
-            case 4: return launch_dec3_v<T, L, 16, 256, 4, 2, 0>(p, prm, s);
-            case 5: return launch_dec3_v<T, L, 32, 512, 8, 1, 1>(p, prm, s);
+            case 1: return launch_dec3_v<T, L, 12, 256, 4, 2, 0>(p, prm, s);
+            case 2: return launch_dec3_v<T, L, 12, 256, 6, 2, 0>(p, prm, s);
+            case 3: return launch_dec3_v<T, L, 12, 256, 12, 2, 0>(p, prm, s);
+            case 4: return launch_dec3_v<T, L, 12, 256, 2, 2, 0>(p, prm, s);
+            case 5: return launch_dec3_v<T, L, 12, 192, 4, 2, 0>(p, prm, s);
+            case 6: return launch_dec3_v<T, L, 12, 192, 6, 3, 0>(p, prm, s);
             default: break;
         }
     }

@@ -84,6 +84,9 @@ int fused_dec_level_part(nddwt_plan *p, int dil, int part, const void *a_in, con
 int fused_rec_stage2(nddwt_plan *p, int dil, const void *u_lo, const void *u_hi, const LevelIO &io, void *a_out,
                      cudaStream_t s);
 
+int fused2d_dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io, void *const *out_bands,
+                      cudaStream_t s);
+int fused2d_rec_level(nddwt_plan *p, int dil, const void *const *in_bands, void *a_out, cudaStream_t s);
 bool fused_is_separable(const nddwt_plan *p);
 int fused_rec_stage2_scatter(nddwt_plan *p, int dil, const void *u_lo, const void *u_hi, void *out, void *over_lo,
                              void *over_hi, cudaStream_t s);

@@ -65,6 +65,7 @@ REF_SHAPES = [
     ((64, 48, 40), "db4", 3, 0),
     ((32, 32, 24, 16), "db4", 3, 1),
     ((4096,), "db8", 6, 0),
+    ((65536,), "db8", 6, 0),                        # one signal of BASELINE configs[1] (the reference has no batch API)
     ((40, 36, 20, 12), "db1", 3, 0),
 ]
 
@@ -101,6 +102,25 @@ def test_fused_equals_generic(sizes, wn, level, l2):
     ya, yb = a.dec(x, level), b.dec(x, level)
     assert orc.rel_l2(ya, yb) <= 2e-6
     assert orc.rel_l2(a.rec(ya), b.rec(ya)) <= 2e-6
+
+
+@pytest.mark.parametrize("wn", ["db1", "db4", "db7", "db10"])
+@pytest.mark.parametrize("dtype", ["complex64", "complex128", "float32", "float64"])
+def test_fused_2d_kernels(wn, dtype):
+    """2-D fused level kernels (any tap length, odd sizes) == generic kernels == oracle."""
+    sizes = (131, 77)
+    prec = _prec(dtype)
+    x = orc.synth(sizes, dtype, 21)
+    a = _obj(sizes, wn, 1, prec, kernel_mode=0)
+    b = _obj(sizes, wn, 1, prec, kernel_mode=1)
+    ya = a.dec(x, 3)
+    assert a._plan(np.iscomplexobj(x), 0).last_path == 1 and b.dec(x, 1) is not None
+    yo = orc.dec_direct(x.astype(np.complex128 if np.iscomplexobj(x) else np.float64), wn, 3, True)
+    assert orc.rel_l2(ya, yo) <= TOL[prec]
+    assert orc.rel_l2(ya, b.dec(x, 3)) <= 10 * TOL[prec]
+    assert orc.rel_l2(a.rec(ya), x) <= TOL[prec]
+    c = orc.synth(yo.shape, dtype, 22)
+    assert orc.rel_l2(a.rec(c), b.rec(c)) <= 10 * TOL[prec]
 
 
 def test_matches_fft_mat_path_and_mex_flow():
@@ -186,3 +206,32 @@ def test_dilated_atrous_mode_opt_in():
     y = o.dec(x, 3)
     assert orc.rel_l2(y, orc.dec_direct(x, "db2", 3, dilations=[1, 2, 4])) <= 1e-12
     assert orc.rel_l2(o.rec(y), x) <= 1e-12
+
+
+def test_4d_full_size_properties_cfg5():
+    """Size-independent properties at BASELINE configs[4]'s full size (192x192x64x48 complex single,
+    db4, 3 levels; the bench.py N=1 workload): perfect reconstruction, linearity, energy."""
+    import torch
+    sizes = [192, 192, 64, 48]
+    if torch.cuda.mem_get_info()[0] < 120e9:
+        pytest.skip("needs ~100 GB of device memory")
+    o = nd.nd_dwt_4D("db4", sizes, "precision", "single", "compute", "gpu", "pres_l2_norm", 1)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    def rnd():
+        t = torch.randn(tuple(reversed(sizes)) + (2,), generator=g, device="cuda", dtype=torch.float32)
+        return torch.view_as_complex(t).permute(3, 2, 1, 0)
+    a = rnd()
+    ya = o.dec(a, 3)
+    assert tuple(ya.shape) == tuple(sizes) + (46,)
+    na = float(torch.linalg.vector_norm(a))
+    assert abs(float(torch.linalg.vector_norm(ya)) / na - 1) <= 1e-4          # P2: Parseval with pres_l2_norm
+    xr = o.rec(ya)
+    assert float(torch.linalg.vector_norm(xr - a)) / na <= 1e-5               # P1
+    del xr
+    b = rnd()
+    yab = o.dec(a + 0.5 * b, 3)
+    yab -= ya
+    del ya
+    yb = o.dec(b, 3)
+    yab -= 0.5 * yb
+    assert float(torch.linalg.vector_norm(yab)) / float(torch.linalg.vector_norm(yb)) <= 1e-5   # linearity
