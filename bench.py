@@ -26,7 +26,7 @@ import numpy as np  # noqa: E402
 WORKLOADS = {
     # name: (sizes, wavelet, levels, dtype)        BASELINE.json configs
     "cfg1": ((256, 256), "db4", 3, "complex128"),
-    "cfg2": ((65536, 4096), "db8", 6, "complex64"),     # 1-D batch (signals along dim 1) -- extension
+    "cfg2": ((65536,), "db8", 6, "complex64", 4096),    # 1-D batch: 4096 signals of 65536 samples (batch extension)
     "cfg3": ((256, 256, 256), "db4", 3, "complex64"),
     "cfg4": ((256, 256, 256, 32), "db4", 3, "complex64"),
     "cfg4s8": ((256, 256, 256, 8), "db4", 3, "complex64"),   # one quarter of cfg4 along dim 4
@@ -96,8 +96,13 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def cpu_reference_pair(sizes, wname, level, dtype, threads, budget_s=25.0):
+def cpu_reference_pair(sizes, wname, level, dtype, threads, budget_s=25.0, batch=1):
     """Time the reference's CPU path on a bounded sample of the workload.  Returns a dict."""
+    if batch > 1:   # the reference has no batch API: loop over a subset of the signals (SURVEY D4)
+        nsig = min(batch, 32)
+        one = cpu_reference_pair(sizes, wname, level, dtype, threads, budget_s=budget_s / nsig, batch=1)
+        one["sample"] = "per-signal loop, %d of %d signals timed as one; " % (1, batch) + one["sample"]
+        return one
     from oracle import nddwt_oracle as orc
     from oracle import ref_mex
     orc.set_fft_workers(threads)
@@ -147,7 +152,7 @@ def cpu_reference_pair(sizes, wname, level, dtype, threads, budget_s=25.0):
 
 
 def run_reference(args, wl_name, wl):
-    sizes, wname, level, dtype = wl
+    sizes, wname, level, dtype = wl[:4]
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -199,8 +204,10 @@ def main():
     import torch
     import nddwt_b200 as nd
 
-    sizes, wname, level, dtype = wl
+    sizes, wname, level, dtype = wl[:4]
+    batch = wl[4] if len(wl) > 4 else 1
     d = len(sizes)
+    full = tuple(sizes) + ((batch,) if batch > 1 else ())       # array shape incl. the batch extension
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU path)"
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
@@ -208,19 +215,19 @@ def main():
     prec = "single" if dtype in ("complex64", "float32") else "double"
     obj = cls(wname, list(sizes), "precision", prec, "compute", "gpu")
     obj.set_kernel_mode(args.kernel_mode)
-    nvox = int(np.prod(sizes))
+    nvox = int(np.prod(full))
     esize = np.dtype(dtype).itemsize
     nb = obj._num_bands(level)
 
     # synthetic input generated on the device (seeded), MATLAB-shaped view of column-major memory
     g = torch.Generator(device=dev).manual_seed(0)
     tdt = {"complex64": torch.float32, "complex128": torch.float64}[dtype]
-    base = torch.randn(tuple(reversed(sizes)) + (2,), generator=g, device=dev, dtype=tdt)
-    x = torch.view_as_complex(base).permute(*reversed(range(d)))
-    plan = obj._plan(True, 0)
-    y_buf = torch.empty((nb,) + tuple(reversed(sizes)), dtype=x.dtype, device=dev)
-    x_out = torch.empty(tuple(reversed(sizes)), dtype=x.dtype, device=dev)
-    xbase = x.permute(*reversed(range(d)))
+    base = torch.randn(tuple(reversed(full)) + (2,), generator=g, device=dev, dtype=tdt)
+    x = torch.view_as_complex(base).permute(*reversed(range(len(full))))
+    plan = obj._plan(True, 0, batch)
+    y_buf = torch.empty((nb,) + tuple(reversed(full)), dtype=x.dtype, device=dev)
+    x_out = torch.empty(tuple(reversed(full)), dtype=x.dtype, device=dev)
+    xbase = x.permute(*reversed(range(len(full))))
     assert xbase.is_contiguous()
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -319,8 +326,8 @@ def main():
         need = 2.2 * (1 + nb) * nvox * esize
         if psutil.virtual_memory().available < need:
             raise MemoryError("host RAM: need %.0f GB pinned" % (need / 1e9))
-        hx = torch.empty(tuple(reversed(sizes)), dtype=x.dtype, pin_memory=True)
-        hy = torch.empty((nb,) + tuple(reversed(sizes)), dtype=x.dtype, pin_memory=True)
+        hx = torch.empty(tuple(reversed(full)), dtype=x.dtype, pin_memory=True)
+        hy = torch.empty((nb,) + tuple(reversed(full)), dtype=x.dtype, pin_memory=True)
         hx.copy_(xbase)
         hx_np = hx.numpy().T
         hy_np = hy.numpy().T
@@ -349,14 +356,14 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
-        cpu = cpu_reference_pair(sizes, wname, level, dtype, len(os.sched_getaffinity(0)))
+        cpu = cpu_reference_pair(sizes, wname, level, dtype, len(os.sched_getaffinity(0)), batch=batch)
 
     line = {
         "metric": "dec+rec Mvoxels/s", "value": value, "unit": "Mvoxels/s", "n_gpus": 1,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": {"complex64": "c64", "complex128": "c128"}[dtype], "data": "synthetic",
-        "config": {"workload": wl_name, "sizes": list(sizes), "wavelet": wname, "levels": level, "bands": nb,
+        "config": {"workload": wl_name, "sizes": list(sizes), "batch": batch, "wavelet": wname, "levels": level, "bands": nb,
                    "elem": dtype, "l2": "working set %.2f GB >> 126 MB L2, no flush" % ((1 + nb) * nvox * esize / 1e9),
                    "pr_rel_err": pr_err, "dec_ms": dec_ms, "rec_ms": rec_ms, "wall_ms_per_step": t_wall / args.steps * 1e3,
                    "step_ms_min_med_max": [min(ms), float(np.median(ms)), max(ms)]},

@@ -82,6 +82,11 @@ NDDWT_API int nddwt_plan_destroy(nddwt_plan *plan);
  * reference parity, nd_dwt_2D.m:183 / nddwt.c:214-228): 1 at every level. */
 NDDWT_API int nddwt_plan_set_dilations(nddwt_plan *plan, const int *dil, int nlevels);
 
+/* Extension (the reference has no batch API): the arrays carry one extra trailing
+ * dimension of `batch` independent signals/images: x is [dims..., batch], the coefficient stack
+ * [dims..., batch, nb].  Batched plans run the generic separable kernels. */
+NDDWT_API int nddwt_plan_set_batch(nddwt_plan *plan, int64_t batch);
+
 /* Selects the kernel family: 0 = auto (fused kernels where an instantiation exists, generic
  * otherwise), 1 = force the generic separable kernels.  Both run on the GPU. */
 NDDWT_API int nddwt_plan_set_kernel_mode(nddwt_plan *plan, int mode);

@@ -136,12 +136,14 @@ class _NdDwtBase:
         self.kernel_mode = 0
 
     # -- plan cache (the stored-filter object on the device) ---------------------------------
-    def _plan(self, is_complex, device_index):
+    def _plan(self, is_complex, device_index, batch=1):
         code, _ = _np_dtype_code(self.precision, is_complex)
-        key = (code, device_index)
+        key = (code, device_index, int(batch))
         pl = self._plans.get(key)
         if pl is None:
             pl = Plan(self.sizes, self.wname, code, self.pres_l2_norm, device_index)
+            if batch != 1:
+                pl.set_batch(batch)
             if self.dilations is not None:
                 pl.set_dilations(self.dilations)
             pl.set_kernel_mode(self.kernel_mode)
@@ -195,8 +197,14 @@ class _NdDwtBase:
         return self._rec_host(np.asarray(y), out)
 
     def _check_x_shape(self, shape):
-        if tuple(shape) != self.sizes:
-            raise ValueError("FIlter size and image size not consistant")
+        """Returns the batch count: 1 for the reference's shapes, B for the batched extension
+        (one extra trailing dimension: x is [sizes, B], coefficients [sizes, B, nb])."""
+        shape = tuple(shape)
+        if shape == self.sizes:
+            return 1
+        if len(shape) == self._ndims + 1 and shape[:-1] == self.sizes:
+            return int(shape[-1])
+        raise ValueError("FIlter size and image size not consistant")
 
     @staticmethod
     def _check_out(out, shape, npdt):
@@ -207,54 +215,55 @@ class _NdDwtBase:
     def _dec_host(self, x, level, out=None):
         if self._ndims == 1 and x.ndim == 2 and 1 in x.shape:
             x = x.reshape(-1)
-        self._check_x_shape(x.shape)
+        batch = self._check_x_shape(x.shape)
         is_c = np.iscomplexobj(x)
         code, npdt = _np_dtype_code(self.precision, is_c)
         xf = np.asfortranarray(x, dtype=npdt)
-        shape = self.sizes + (self._num_bands(level),)
+        shape = tuple(x.shape) + (self._num_bands(level),)
         y = np.empty(shape, dtype=npdt, order="F") if out is None else self._check_out(out, shape, np.dtype(npdt))
-        self._plan(is_c, 0).dec_host(xf.ctypes.data, y.ctypes.data, level)
+        self._plan(is_c, 0, batch).dec_host(xf.ctypes.data, y.ctypes.data, level)
         return y
 
     def _rec_host(self, y, out=None):
-        if y.ndim != self._ndims + 1:
+        if y.ndim not in (self._ndims + 1, self._ndims + 2):
             raise ValueError("FIlter size and image size not consistant")
-        self._check_x_shape(y.shape[:-1])
+        batch = self._check_x_shape(y.shape[:-1])
         level = self._level_of(y.shape[-1])
         is_c = np.iscomplexobj(y)
         code, npdt = _np_dtype_code(self.precision, is_c)
         yf = np.asfortranarray(y, dtype=npdt)
-        x = np.empty(self.sizes, dtype=npdt, order="F") if out is None else self._check_out(out, self.sizes, np.dtype(npdt))
-        self._plan(is_c, 0).rec_host(yf.ctypes.data, x.ctypes.data, level)
+        xs = tuple(y.shape[:-1])
+        x = np.empty(xs, dtype=npdt, order="F") if out is None else self._check_out(out, xs, np.dtype(npdt))
+        self._plan(is_c, 0, batch).rec_host(yf.ctypes.data, x.ctypes.data, level)
         return x
 
     def _dec_device(self, x, level):
-        self._check_x_shape(x.shape)
+        batch = self._check_x_shape(x.shape)
         is_c = x.is_complex()
         code, _ = _np_dtype_code(self.precision, is_c)
         tdt = _TORCH_OF[code]
         base = _colmajor_base(x.to(tdt))
         dev = x.device.index or 0
-        out = torch.empty((self._num_bands(level),) + tuple(reversed(self.sizes)), dtype=tdt, device=x.device)
+        out = torch.empty((self._num_bands(level),) + tuple(reversed(tuple(x.shape))), dtype=tdt, device=x.device)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            self._plan(is_c, dev).dec(base.data_ptr(), out.data_ptr(), level, stream)
+            self._plan(is_c, dev, batch).dec(base.data_ptr(), out.data_ptr(), level, stream)
         return out.permute(*reversed(range(out.dim())))
 
     def _rec_device(self, y):
-        if y.dim() != self._ndims + 1:
+        if y.dim() not in (self._ndims + 1, self._ndims + 2):
             raise ValueError("FIlter size and image size not consistant")
-        self._check_x_shape(y.shape[:-1])
+        batch = self._check_x_shape(y.shape[:-1])
         level = self._level_of(y.shape[-1])
         is_c = y.is_complex()
         code, _ = _np_dtype_code(self.precision, is_c)
         tdt = _TORCH_OF[code]
         base = _colmajor_base(y.to(tdt))
         dev = y.device.index or 0
-        out = torch.empty(tuple(reversed(self.sizes)), dtype=tdt, device=y.device)
+        out = torch.empty(tuple(reversed(tuple(y.shape[:-1]))), dtype=tdt, device=y.device)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            self._plan(is_c, dev).rec(base.data_ptr(), out.data_ptr(), level, stream)
+            self._plan(is_c, dev, batch).rec(base.data_ptr(), out.data_ptr(), level, stream)
         return out.permute(*reversed(range(out.dim())))
 
     def launches(self):

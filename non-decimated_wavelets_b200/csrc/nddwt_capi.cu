@@ -51,7 +51,8 @@ static int ensure_approx(nddwt_plan *p, int which)
 static int dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io, void *const *out_bands,
                      cudaStream_t s)
 {
-    if (p->kernel_mode == 0) {
+    if (p->batch > 1 && (io.halo_lo || io.halo_hi)) { set_error("slabs of batched plans are not supported"); return NDDWT_ERR_ARG; }
+    if (p->kernel_mode == 0 && p->batch == 1) {
         int rc = fused_dec_level(p, dil, a_in, io, out_bands, s);
         if (rc <= 0) { p->last_path = 1; return rc; }
         rc = fused2d_dec_level(p, dil, a_in, io, out_bands, s);
@@ -63,7 +64,7 @@ static int dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io
 
 static int rec_level(nddwt_plan *p, int dil, const void *const *in_bands, void *a_out, cudaStream_t s)
 {
-    if (p->kernel_mode == 0) {
+    if (p->kernel_mode == 0 && p->batch == 1) {
         int rc = fused_rec_level(p, dil, in_bands, a_out, s);
         if (rc <= 0) { p->last_path = 1; return rc; }
         rc = fused2d_rec_level(p, dil, in_bands, a_out, s);
@@ -232,6 +233,22 @@ int nddwt_plan_set_dilations(nddwt_plan *p, const int *dil, int nlevels)
     return 0;
 }
 
+int nddwt_plan_set_batch(nddwt_plan *p, int64_t batch)
+{
+    if (!p || batch < 1) { set_error("batch must be >= 1"); return NDDWT_ERR_ARG; }
+    if (batch == p->batch) return 0;
+    cudaSetDevice(p->device);
+    // scratch is sized by numel: drop it, it is re-allocated on the next call
+    for (int i = 0; i < 2; ++i) if (p->approx[i]) { cudaFree(p->approx[i]); p->approx[i] = nullptr; }
+    if (p->gen_scratch) { cudaFree(p->gen_scratch); p->gen_scratch = nullptr; }
+    if (p->fused_scratch) { cudaFree(p->fused_scratch); p->fused_scratch = nullptr; p->fused_scratch_bytes = 0; }
+    if (p->host_x) { cudaFree(p->host_x); p->host_x = nullptr; }
+    if (p->host_c) { cudaFree(p->host_c); p->host_c = nullptr; p->host_c_bytes = 0; }
+    p->numel = p->numel / p->batch * batch;
+    p->batch = batch;
+    return 0;
+}
+
 int nddwt_plan_set_kernel_mode(nddwt_plan *p, int mode)
 {
     if (!p || mode < 0 || mode > 1) { set_error("bad kernel mode"); return NDDWT_ERR_ARG; }
@@ -280,6 +297,10 @@ int nddwt_dec(nddwt_plan *p, const void *x_dev, void *coeffs_dev, int level, voi
     if (!x_dev || !coeffs_dev) { set_error("null device pointer"); return NDDWT_ERR_ARG; }
     NDDWT_CUDA(cudaSetDevice(p->device));
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (p->ndims == 1) {   // 1-D: the whole multi-level cascade is one kernel
+        rc = fused1d_transform(p, false, x_dev, coeffs_dev, level, s);
+        if (rc <= 0) { p->last_path = 1; return rc; }
+    }
     const int nd = 1 << p->ndims;
     char *c = reinterpret_cast<char *>(coeffs_dev);
     const size_t band_bytes = (size_t)p->numel * p->esize;
@@ -313,6 +334,10 @@ int nddwt_rec(nddwt_plan *p, const void *coeffs_dev, void *x_dev, int level, voi
     if (!x_dev || !coeffs_dev) { set_error("null device pointer"); return NDDWT_ERR_ARG; }
     NDDWT_CUDA(cudaSetDevice(p->device));
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (p->ndims == 1) {
+        rc = fused1d_transform(p, true, coeffs_dev, x_dev, level, s);
+        if (rc <= 0) { p->last_path = 1; return rc; }
+    }
     const int nd = 1 << p->ndims;
     const char *c = reinterpret_cast<const char *>(coeffs_dev);
     const size_t band_bytes = (size_t)p->numel * p->esize;

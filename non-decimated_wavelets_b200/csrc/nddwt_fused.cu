@@ -1712,7 +1712,7 @@ static int dispatch_rec_last_scatter(nddwt_plan *p, const void *u_lo, const void
 
 static bool fused_geometry_ok(const nddwt_plan *p)
 {
-    if (p->ndims < 3) return false;
+    if (p->ndims < 3 || p->batch != 1) return false;
     if (p->dims[0] * p->dims[1] >= (int64_t)1 << 30) return false;
     if (p->dims[0] < p->L[0] || p->dims[1] < p->L[1]) return false;
     if (p->dims[0] % (16 / (int64_t)p->esize) != 0) return false;   // 16-byte rows (vector stores, bulk copies)
@@ -1760,7 +1760,7 @@ int accumulate_elems(nddwt_plan *p, void *dst, const void *src, int64_t nelem, c
 
 bool fused_is_separable(const nddwt_plan *p)
 {
-    if (p->kernel_mode != 0 || p->ndims != 4 || !uniform_taps(p) || !fused_geometry_ok(p)) return false;
+    if (p->kernel_mode != 0 || p->batch != 1 || p->ndims != 4 || !uniform_taps(p) || !fused_geometry_ok(p)) return false;
     for (int j = 0; j < NDDWT_MAX_LEVELS; ++j)
         if (p->dil[j] != 1) return false;
     return p->L[0] == 2 || p->L[0] == 4 || p->L[0] == 6 || p->L[0] == 8;

@@ -209,7 +209,7 @@ static int dispatch_rec2(nddwt_plan *p, const void *const *in_bands, void *a_out
 
 static bool ok2d(const nddwt_plan *p, int dil, const LevelIO *io)
 {
-    if (dil != 1 || p->ndims != 2 || p->L[0] != p->L[1]) return false;
+    if (dil != 1 || p->ndims != 2 || p->batch != 1 || p->L[0] != p->L[1]) return false;
     if (io && (io->halo_lo || io->halo_hi)) return false;      // slabs of 2-D arrays use the generic kernels
     return p->dims[0] * p->dims[1] < ((int64_t)1 << 40);
 }

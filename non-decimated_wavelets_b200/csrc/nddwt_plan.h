@@ -13,7 +13,8 @@ struct nddwt_plan {
     int dtype = NDDWT_C64;
     int pres_l2 = 0;
     int device = 0;
-    int64_t numel = 0;     // prod(dims)
+    int64_t numel = 0;     // prod(dims) * batch
+    int64_t batch = 1;     // trailing batch dimension (extension: the reference has no batch API)
     size_t esize = 0;      // bytes per element
 
     // unscaled wave_filters output per dim
@@ -87,6 +88,7 @@ int fused_rec_stage2(nddwt_plan *p, int dil, const void *u_lo, const void *u_hi,
 int fused2d_dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io, void *const *out_bands,
                       cudaStream_t s);
 int fused2d_rec_level(nddwt_plan *p, int dil, const void *const *in_bands, void *a_out, cudaStream_t s);
+int fused1d_transform(nddwt_plan *p, bool rec, const void *in, void *out, int level, cudaStream_t s);
 bool fused_is_separable(const nddwt_plan *p);
 int fused_rec_stage2_scatter(nddwt_plan *p, int dil, const void *u_lo, const void *u_hi, void *out, void *over_lo,
                              void *over_hi, cudaStream_t s);

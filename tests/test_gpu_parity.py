@@ -235,3 +235,39 @@ def test_4d_full_size_properties_cfg5():
     yb = o.dec(b, 3)
     yab -= 0.5 * yb
     assert float(torch.linalg.vector_norm(yab)) / float(torch.linalg.vector_norm(yb)) <= 1e-5   # linearity
+
+
+@pytest.mark.parametrize("sizes,wn,level,batch", [((4096,), "db8", 6, 8), ((64, 48), ["db2", "db3"], 2, 5),
+                                                    ((32, 24, 16), "db4", 2, 3)])
+def test_batched_extension(sizes, wn, level, batch):
+    """Batch API (extension): x is [sizes, B]; every slice equals the un-batched transform."""
+    x = orc.synth(tuple(sizes) + (batch,), np.complex64, 31)
+    o = _obj(sizes, wn, 0, "single")
+    y = o.dec(x, level)
+    nb = orc.num_bands(len(sizes), level)
+    assert y.shape == tuple(sizes) + (batch, nb)
+    for b in (0, batch - 1):
+        yo = orc.dec_direct(x[..., b].astype(np.complex128), wn, level)
+        assert orc.rel_l2(y[..., b, :], yo) <= 1e-5
+    assert orc.rel_l2(o.rec(y), x) <= 1e-5
+
+
+@pytest.mark.parametrize("n,wn,level", [(54321, "db1", 4), (4099, "db8", 6), (300, "db10", 3), (61, "db3", 5), (65536, "db4", 8)])
+@pytest.mark.parametrize("dtype", ["complex64", "float64"])
+def test_fused_1d_cascade(n, wn, level, dtype):
+    """1-D cascade kernel (all levels in one launch) == generic per-level kernels == oracle."""
+    prec = _prec(dtype)
+    x = orc.synth((n,), dtype, 41)
+    a = _obj((n,), wn, 1, prec, kernel_mode=0)
+    b = _obj((n,), wn, 1, prec, kernel_mode=1)
+    ya = a.dec(x, level)
+    pa = a._plan(np.iscomplexobj(x), 0)
+    l0 = pa.launches
+    ya = a.dec(x, level)
+    assert pa.launches - l0 == 1 and pa.last_path == 1
+    yo = orc.dec_direct(x.astype(np.complex128 if np.iscomplexobj(x) else np.float64), wn, level, True)
+    assert orc.rel_l2(ya, yo) <= TOL[prec]
+    assert orc.rel_l2(ya, b.dec(x, level)) <= 10 * TOL[prec]
+    assert orc.rel_l2(a.rec(ya), x) <= TOL[prec]
+    c = orc.synth(yo.shape, dtype, 42)
+    assert orc.rel_l2(a.rec(c), b.rec(c)) <= 10 * TOL[prec]
