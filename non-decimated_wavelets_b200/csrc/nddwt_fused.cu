@@ -1175,20 +1175,21 @@ static FusedTaps<T, L> make_taps(const nddwt_plan *p, bool rec)
 
 static int pick_zc(int n3, int tiles, int H, int ctas_per_wave)
 {
-    // choose planes per chunk: enough CTAs to fill the machine several times, while keeping the
-    // ring warm-up (L planes re-read per chunk) a small fraction of the chunk
+    // balanced chunks of the marching dimension: enough CTAs to fill the machine in whole waves,
+    // while keeping the ring warm-up (L planes re-read per chunk, loads only) a small fraction
     int best = n3;
     double best_cost = 1e30;
-    for (int zc = 4; zc <= n3; ++zc) {
-        const int nch = (n3 + zc - 1) / zc;
-        const double ctas = (double)tiles * nch;
+    for (int nch = 1; nch <= n3; ++nch) {
+        const int zc = (n3 + nch - 1) / nch;
+        if (zc < 4 && nch > 1) break;
+        const int real_nch = (n3 + zc - 1) / zc;
+        const double ctas = (double)tiles * real_nch;
         const double waves = ctas / ctas_per_wave;
         const double eff = waves / (double)((int64_t)(waves + 0.999999));   // tail efficiency
         const double work = (double)(zc + 0.35 * (H + 1)) / zc;              // warm-up overhead (loads only)
         const double cost = work / eff;
         if (cost < best_cost - 1e-9) { best_cost = cost; best = zc; }
     }
-    if (n3 < 4) best = n3;
     return best;
 }
 
@@ -1204,11 +1205,7 @@ static int launch_dec3_v(nddwt_plan *p, const Dec3Params<T> &base, cudaStream_t 
     prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
     prm.halo_below = (L / 2 - 1);
     auto kern = k_dec3_fused<T, L, T2, NT, R2, MINB, CWSEL>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-        attr_done = true;
-    }
+    NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));   // per-device attribute: set on every launch
     const FusedTaps<T, L> tp = make_taps<T, L>(p, false);
     const int64_t grid = (int64_t)prm.tiles1 * prm.tiles2 * prm.nchunks * batches;
     {
@@ -1306,11 +1303,7 @@ static int launch_rec3_v(nddwt_plan *p, const Rec3Params<T> &base, cudaStream_t 
         prm.prefetch = pf;
     }
     auto kern = k_rec3_fused<T, L, T2, NT, R2, MINB>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-        attr_done = true;
-    }
+    NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));   // per-device attribute: set on every launch
     const FusedTaps<T, L> tp = make_taps<T, L>(p, true);
     const int64_t grid = (int64_t)prm.tiles1 * prm.tiles2 * prm.nchunks * batches;
     {
@@ -1394,11 +1387,7 @@ static int launch_rec3_bulk(nddwt_plan *p, const Rec3Params<T> &base, cudaStream
         }
     }
     auto kern = k_rec3_bulk<T, L, T2, NT, R2, MINB>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-        attr_done = true;
-    }
+    NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));   // per-device attribute: set on every launch
     const FusedTaps<T, L> tp = make_taps<T, L>(p, true);
     const int64_t grid = (int64_t)prm.tiles1 * prm.tiles2 * prm.nchunks * batches;
     {

@@ -140,11 +140,7 @@ static int launch_dec2(nddwt_plan *p, const void *a_in, void *const *out_bands, 
     const int n1 = (int)p->dims[0], n2 = (int)p->dims[1];
     const size_t smem = (size_t)((TY + H) * P + 2 * TY * P) * sizeof(T);
     auto kern = k_dec2_fused<T, L, TX, TY, NT>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per-device attribute: set on every launch
     dim3 grid((n1 + TX - 1) / TX, (n2 + TY - 1) / TY);
     {
         LaunchTimer lt(p, KIND_DEC3, s);
@@ -164,11 +160,7 @@ static int launch_rec2(nddwt_plan *p, const void *const *in_bands, void *a_out, 
     const int n1 = (int)p->dims[0], n2 = (int)p->dims[1];
     const size_t smem = (size_t)(4 * (TY + H) * P + 2 * TY * P) * sizeof(T);
     auto kern = k_rec2_fused<T, L, TX, TY, NT>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per-device attribute: set on every launch
     dim3 grid((n1 + TX - 1) / TX, (n2 + TY - 1) / TY);
     {
         LaunchTimer lt(p, KIND_REC3, s);
