@@ -1,23 +1,26 @@
-// nddwt_fused.cu -- fused per-level kernels for sm_100a: one launch reads the approximation band
-// once and writes all 2^d subbands once (analysis), or reads the 2^d subbands once and writes the
-// reconstructed band once (synthesis).  Direct separable circular lo/hi filtering; no FFT, no
-// stored Fourier-domain filters, no tensor cores (short-filter stencil).
+// nddwt_fused.cu -- fused per-level kernels for 3-D and 4-D arrays on sm_100a: one launch reads the
+// approximation band once and writes all 2^3 subbands once (analysis), or reads the subbands once
+// and writes the reconstructed band once (synthesis).  Direct separable circular lo/hi filtering;
+// no FFT, no stored Fourier-domain filters, no tensor cores (short-filter stencil).
 //
 // Replaces, per level: nd_dwt_dec_1level / nd_dwt_rec_1level (mex/nddwt.c:98-186) and
-// level_1_dec / level_1_rec of Functions/nd_dwt_3D.m:345-393 (and siblings).
+// level_1_dec / level_1_rec of Functions/nd_dwt_3D.m:345-393 and nd_dwt_4D.m:394-467.
 //
-// Analysis kernel (3-D tile pipeline, also the back end of the 4-D path):
+// k_dec3_fused  (analysis tile kernel, also the back end of the 4-D path)
 //   * a CTA owns a T1 x T2 column of the (dim1, dim2) plane and marches along dim 3;
-//   * stage A  (dim 3): each thread keeps an L-deep ring of input planes in REGISTERS for its
-//     (T1+L-1) x (T2+L-1) haloed positions, loads one new plane per step straight from global
-//     memory (coalesced along dim 1, periodic wrap folded into precomputed offsets) and emits the
-//     lo3 / hi3 planes into shared memory;
-//   * stage B  (dim 1): 16-byte shared-memory chunks, each thread produces 2*VEC consecutive
-//     outputs for lo1 / hi1 (an XOR chunk swizzle keeps the quarter-warp accesses conflict-free);
-//   * stage C  (dim 2): lanes run along dim 1, each thread slides a register window down R2 rows
-//     and streams the 8 subbands to global memory with fully coalesced st.global.cs.
-//   complex-single arithmetic is FFMA2 (fma.rn.f32x2) on (re, im) pairs with duplicated taps
-//   taken from the kernel-parameter constant bank.
+//   * stage A (dim 3): each thread keeps an L-deep ring of input planes in REGISTERS for its
+//     (T1+L-1) x (T2+L-1) haloed positions; the next plane is loaded a full step ahead straight
+//     from global memory (coalesced along dim 1, periodic wrap folded into precomputed offsets);
+//   * stage B (dim 1): 16-byte shared-memory chunks, lanes run along rows, odd chunk pitch =>
+//     conflict-free; each thread produces 2*VEC consecutive outputs for lo1 / hi1;
+//   * stage C (dim 2): lanes run along dim 1, sliding register window down the rows, the 8
+//     subbands leave through 16-byte st.global.cs streaming stores;
+//   * complex-single arithmetic is FFMA2 (fma.rn.f32x2) on (re, im) pairs with duplicated taps
+//     taken from the kernel-parameter constant bank; all index math is hoisted out of the march.
+// k_rec3_bulk   (synthesis tile kernel): TMA-staged (cp.async.bulk.tensor / cp.async.bulk + mbarrier)
+//   haloed subband tiles, stages RA (dim 2) / RB (dim 1) / RC (dim 3, scatter ring of partial sums).
+// k_rec3_fused  : the same pipeline with direct ld.global.nc loads (rows narrower than a staged tile).
+// k_dec_last / k_rec_last[_scatter] : dim-4 passes of the 4-D path and slab-exchange points (multi-GPU).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -70,8 +73,6 @@ __device__ __forceinline__ int wrapi(int m, int n)
     m %= n;
     return m < 0 ? m + n : m;
 }
-
-__device__ __forceinline__ int swz(int chunk) { return chunk ^ ((chunk >> 3) & 1); }
 
 template <typename T> __device__ __forceinline__ T ldg_stream(const T *p) { return __ldg(p); }
 
