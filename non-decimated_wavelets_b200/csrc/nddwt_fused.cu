@@ -161,16 +161,20 @@ struct DispatchA<T, L, PPT, L> {
                                                const int (&)[PPT], int, const T *) {}
 };
 
-template <typename T, int L, int T2, int NT, int R2, int MINB, int CWSEL = 0>
+template <typename T, int L, int T2, int NT, int R2, int MINB, int CWSEL = 0, int RBM = 1>
 __global__ void __launch_bounds__(NT, MINB)
 k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
 {
     using G = Geo<T, L, T2>;
-    constexpr int VEC = G::VEC, R1 = G::R1, T1 = G::T1, HB = G::HB, HA = G::HA;
-    constexpr int W1 = G::W1, W2 = G::W2, W2P = G::W2P, PA = G::PA, PB = G::PB, NPOS = G::NPOS, NCH = G::NCH;
+    constexpr int VEC = G::VEC, T1 = G::T1, HB = G::HB, HA = G::HA;
+    constexpr int R1 = RBM * G::R1;                         // dim-1 outputs per stage-B item (RBM = 2: half the items, 2/3 of the shared-memory reads)
+    constexpr int NCB = T1 / R1;                            // stage-B items per row
+    constexpr int NCH = (R1 + L - 1 + VEC - 1) / VEC;       // chunks read per stage-B item
+    constexpr int W1 = G::W1, W2 = G::W2, W2P = G::W2P, PA = G::PA, PB = G::PB, NPOS = G::NPOS;
     constexpr int PPT = (NPOS + NT - 1) / NT;
     constexpr int NRUN = T2 / R2;
-    constexpr int NB_ITEMS = 2 * 8 * W2P, KB = (NB_ITEMS + NT - 1) / NT;
+    constexpr int NB_ITEMS = 2 * NCB * W2P, KB = (NB_ITEMS + NT - 1) / NT;
+    static_assert((NCB - 1) * R1 + NCH * VEC <= PA, "stage-B reads stay inside the SA row pitch");
     constexpr int CW = (CWSEL == 1) ? 1 : VEC;              // columns per stage-C item (16-byte chunk or one element)
     constexpr int CPR = T1 / CW;                            // stage-C items per row
     constexpr int NC_ITEMS = 4 * NRUN * CPR, KC = (NC_ITEMS + NT - 1) / NT;
@@ -225,7 +229,7 @@ k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
     for (int k = 0; k < KB; ++k) {
         const int it = tid + k * NT;
         const int r = it % W2P, g = it / W2P;
-        const int cb = g & 7, a = g >> 3;
+        const int cb = g % NCB, a = g / NCB;
         if (it < NB_ITEMS && r < W2) b_mask |= 1 << k;
         b_src[k] = (a * W2 + r) * PA + cb * R1;
         b_dst[k] = (2 * a * W2 + r) * PB + cb * R1;
@@ -283,16 +287,16 @@ k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
 #pragma unroll
                     for (int j = 0; j < L; ++j) macp(acc[o], tp.lo[0][L - 1 - j], v[o + j]);
                 }
-                st_chunk<T, VEC>(d0, acc);
-                st_chunk<T, VEC>(d0 + VEC, acc + VEC);
+#pragma unroll
+                for (int c = 0; c < R1 / VEC; ++c) st_chunk<T, VEC>(d0 + c * VEC, acc + c * VEC);
 #pragma unroll
                 for (int o = 0; o < R1; ++o) {
                     acc[o] = zero_of(T());
 #pragma unroll
                     for (int j = 0; j < L; ++j) macp(acc[o], tp.hi[0][L - 1 - j], v[o + j]);
                 }
-                st_chunk<T, VEC>(d0 + W2 * PB, acc);
-                st_chunk<T, VEC>(d0 + W2 * PB + VEC, acc + VEC);
+#pragma unroll
+                for (int c = 0; c < R1 / VEC; ++c) st_chunk<T, VEC>(d0 + W2 * PB + c * VEC, acc + c * VEC);
             }
         }
         __syncthreads();
@@ -1004,6 +1008,482 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp, const __grid_consta
 
 
 // ---------------------------------------------------------------------------------------------
+// Synthesis tile kernel, second generation (8-byte elements).  k_rec3_bulk turned out to be bound by
+// the shared-memory data pipe (ncu: ~2000 wavefronts per plane-tile, 22 % of them bank conflicts of
+// the halo-column tail warps), not by HBM or FMA issue.  Same staging (TMA tensor maps / bulk row
+// copies + mbarrier) and the same scatter ring for dim 3, but the two shared-memory stages move
+// fewer bytes:
+//   stage RA: one thread per (q, haloed column) runs the FULL tile height with a sliding L-row
+//             window per band, so every staged element is read exactly once (was (R2+L-1)/R2 times);
+//             column groups are padded to whole 128-byte wavefronts (GP lanes) => no bank conflicts;
+//   stage RB: 4*VEC outputs per item (was 2*VEC): (4*VEC+L-1) inputs per 4*VEC outputs.
+template <typename T, int L, int T2>
+struct GeoRB2 : GeoRB<T, L, T2> {
+    using B = GeoRB<T, L, T2>;
+    static constexpr int LPW = 128 / (int)sizeof(T);                  // lanes per conflict-free wavefront
+    static constexpr int GP = (B::W1 + LPW - 1) / LPW * LPW;          // padded lanes per (q) column group
+    static constexpr int NA_SLOTS = 4 * GP;
+    static constexpr int R1B = 4 * B::VEC;                            // stage-RB outputs per item
+    static constexpr int NCB = B::T1 / R1B;                           // items per row
+    static constexpr int NCHB = (R1B + L - 1 + B::VEC - 1) / B::VEC;  // chunks read per item
+    static constexpr int NB_ITEMS = 2 * NCB * T2;
+    static_assert((NCB - 1) * R1B + NCHB * B::VEC <= B::PU, "stage-RB reads stay inside the SU row pitch");
+};
+
+template <typename T, int L, int T2, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_rec3_bulk2(const Rec3Params<T> p, const FusedTaps<T, L> tp, const __grid_constant__ TmaMaps maps)
+{
+    using G = GeoRB2<T, L, T2>;
+    constexpr int VEC = G::VEC, T1 = G::T1, HB = G::HB, HBAL = G::HBAL, SHIFT = G::SHIFT;
+    constexpr int W1 = G::W1, W2 = G::W2, W1S = G::W1S, PU = G::PU, PV = G::PV;
+    constexpr int GP = G::GP, R1B = G::R1B, NCB = G::NCB, NCHB = G::NCHB, NB_ITEMS = G::NB_ITEMS;
+    constexpr int NC_ITEMS = T2 * 16, KC = (NC_ITEMS + NT - 1) / NT;
+    constexpr int NROWS = 8 * W2, KR = (NROWS + NT - 1) / NT;       // staged rows per plane
+    constexpr uint32_t PLANE_BYTES = G::PLANE_BYTES;
+    constexpr int BP = G::BP;
+    static_assert(G::NA_SLOTS <= NT && NB_ITEMS <= NT, "one stage-RA / stage-RB item per thread");
+    static_assert(T2 % 8 == 0, "tile rows");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T *RAW = reinterpret_cast<T *>(smem_raw);          // [8][W2][W1S]  haloed subband tiles of one plane
+    T *SU = RAW + G::RAW_ELEMS;                         // [4][T2][PU]
+    T *SV = SU + 4 * T2 * PU;                           // [2][T2][PV]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(SV + 2 * T2 * PV);
+
+    const int tid = threadIdx.x;
+    int bid = blockIdx.x;
+    const int t1 = bid % p.tiles1;
+    bid /= p.tiles1;
+    const int t2 = bid % p.tiles2;
+    bid /= p.tiles2;
+    const int chunk = bid % p.nchunks;
+    const int batch = bid / p.nchunks;
+    const int a1 = t1 * T1, a2 = t2 * T2;
+    const int z0 = chunk * p.zc;
+    const int z1 = min(z0 + p.zc, p.n3);
+    const int n1 = p.n1, n2 = p.n2, n3 = p.n3;
+    const int64_t s3 = p.s3;
+    const int bsel = batch / p.nhyp, bhyp = batch - bsel * p.nhyp;
+    const int64_t boff = (int64_t)bhyp * p.s4;
+
+    const bool use_tma = p.prefetch == 3 && (a1 - HBAL >= 0) && (a1 - HBAL + W1S <= n1) && (a2 - HB >= 0) &&
+                         (a2 - HB + W2 <= n2);
+    // ---- hoisted per-thread constants ----
+    // row copies of edge tiles: (band b, haloed row r) -> up to two contiguous segments (periodic wrap along dim 1)
+    const T *r_src[KR];
+    int r_dst[KR];
+    const int r_gc0 = wrapi(a1 - HBAL, n1);
+    const int r_len0 = min(W1S, n1 - r_gc0);
+#pragma unroll
+    for (int k = 0; k < KR; ++k) {
+        constexpr int NW = NT / 32;
+        const int slot = tid + k * NT;
+        const int it = (slot % 32) * NW + (slot / 32) % NW + (slot / NT) * NT;   // round-robin over the warps
+        const int r = it % W2, b = (it < NROWS) ? it / W2 : 0;
+        const int grow = wrapi(a2 - HB + r, n2);
+        r_src[k] = p.in[8 * bsel + b] + boff + (int64_t)grow * n1;
+        r_dst[k] = (it < NROWS) ? b * BP + r * W1S : -1;
+    }
+    // stage RA: thread = (q = b1 + 2 b3, haloed column c), groups padded to GP lanes
+    const int a_q = tid / GP, a_c = tid - a_q * GP;
+    const bool a_on = (tid < G::NA_SLOTS) && (a_c < W1);
+    const int a_qq = a_on ? a_q : 0, a_cc = a_on ? a_c : 0;
+    const int a_src = ((a_qq & 1) + 4 * (a_qq >> 1)) * BP + SHIFT + a_cc;
+    const int a_dst = a_qq * T2 * PU + a_cc;
+    // stage RB: item = (b3, group of R1B outputs cb, row j); lanes run along rows; the upper threads take it
+    const int b_it = tid - (NT - NB_ITEMS);
+    const bool b_on = b_it >= 0;
+    const int b_j = (b_on ? b_it : 0) % T2, b_g = (b_on ? b_it : 0) / T2;
+    const int b_cb = b_g % NCB, b_b3 = b_g / NCB;
+    const int b_src = (2 * b_b3 * T2 + b_j) * PU + b_cb * R1B;
+    const int b_dst = (b_b3 * T2 + b_j) * PV + b_cb * R1B;
+    // stage RC: thread owns KC 16-byte output chunks and their L-deep rings of partial sums
+    int c_src[KC];
+    T *c_out[KC];
+    bool c_ok[KC];
+    T acc[KC][L][VEC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        const int it = tid + k * NT;
+        const int cp = it & 15, j = (it >> 4) % T2;
+        c_src[k] = j * PV + cp * VEC;
+        const int g1 = a1 + cp * VEC, g2 = a2 + j;
+        c_ok[k] = (it < NC_ITEMS) && g1 < n1 && g2 < n2;
+        c_out[k] = p.out[bsel] + boff + ((int64_t)z0 - (L - 1)) * s3 + (int64_t)g2 * n1 + g1;
+#pragma unroll
+        for (int s = 0; s < L; ++s)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[k][s][e] = zero_of(T());
+    }
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue_plane = [&](int zi) {   // caller has already posted expect_tx and synchronised the CTA
+        if (use_tma) {
+            if (tid == 0) {
+                const int zp = bhyp * n3 + zi;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) tma_load_3d(RAW + b * BP, &maps.m[8 * bsel + b], a1 - HBAL, a2 - HB, zp, bar);
+            }
+        } else {
+            const int64_t zoff = (int64_t)zi * s3;
+#pragma unroll
+            for (int k = 0; k < KR; ++k) {
+                if (r_dst[k] >= 0) {
+                    const T *src = r_src[k] + zoff;
+                    T *dst = RAW + r_dst[k];
+                    bulk_g2s(dst, src + r_gc0, (uint32_t)(r_len0 * sizeof(T)), bar);
+                    if (r_len0 < W1S) bulk_g2s(dst + r_len0, src, (uint32_t)((W1S - r_len0) * sizeof(T)), bar);
+                }
+            }
+        }
+    };
+
+    // single chunk = the whole periodic dimension: every coefficient plane is staged exactly once (periodic
+    // closure, see k_rec3_bulk)
+    const bool closed = (p.nchunks == 1);
+    const int nsteps = closed ? (z1 - z0) : (z1 - z0) + L - 1;
+    if (tid == 0) mbar_expect_tx(bar, PLANE_BYTES);
+    __syncthreads();   // the expect_tx must precede every complete_tx of the phase
+    issue_plane(wrapi(z0 - HB, n3));
+
+    int u = 0;
+    uint32_t parity = 0;
+    for (int t = 0; t < nsteps; ++t) {
+        mbar_wait(bar, parity);
+        parity ^= 1;
+
+        // ---- stage RA: dim 2, full tile height, sliding window over the staged rows of both b2 bands
+        if (a_on) {
+            const T *s0 = RAW + a_src;
+            const T *s1 = s0 + 2 * BP;
+            T *dst = SU + a_dst;
+            T w0[L], w1[L];
+#pragma unroll
+            for (int i = 0; i < L - 1; ++i) {
+                w0[i] = s0[i * W1S];
+                w1[i] = s1[i * W1S];
+            }
+#pragma unroll
+            for (int i = 0; i < T2; ++i) {
+                w0[(i + L - 1) % L] = s0[(i + L - 1) * W1S];
+                w1[(i + L - 1) % L] = s1[(i + L - 1) * W1S];
+                T o0 = zero_of(T()), o1 = zero_of(T());
+#pragma unroll
+                for (int kk = 0; kk < L; ++kk) {
+                    macp(o0, tp.lo[1][kk], w0[(i + kk) % L]);
+                    macp(o1, tp.hi[1][kk], w1[(i + kk) % L]);
+                }
+                dst[i * PU] = add(o0, o1);
+            }
+        }
+        __syncthreads();   // RAW fully consumed, SU complete
+
+        // ---- stage the next coefficient plane while RB / RC run
+        if (t + 1 < nsteps) {
+            if (tid == 0) mbar_expect_tx(bar, PLANE_BYTES);
+            issue_plane(wrapi(z0 - HB + t + 1, n3));
+        }
+
+        // ---- stage RB: dim 1
+        if (b_on) {
+            T o[R1B];
+#pragma unroll
+            for (int i = 0; i < R1B; ++i) o[i] = zero_of(T());
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {
+                const T *row = SU + b_src + hb * T2 * PU;
+                const typename TapOf<T>::type *g = hb ? tp.hi[0] : tp.lo[0];
+                T v[NCHB * VEC];
+#pragma unroll
+                for (int j = 0; j < NCHB; ++j) ld_chunk<T, VEC>(row + j * VEC, v + j * VEC);
+#pragma unroll
+                for (int i = 0; i < R1B; ++i)
+#pragma unroll
+                    for (int kk = 0; kk < L; ++kk) macp(o[i], g[kk], v[i + kk]);
+            }
+#pragma unroll
+            for (int j = 0; j < R1B / VEC; ++j) st_chunk<T, VEC>(SV + b_dst + j * VEC, o + j * VEC);
+        }
+        __syncthreads();
+
+        // ---- stage RC: dim 3 scatter ring
+        const bool store = closed || (t >= L - 1);
+        const int64_t wrap_off = (closed && t < L - 1) ? (int64_t)n3 * s3 : 0;   // early partials of the wrapped planes
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            if (tid + k * NT < NC_ITEMS) {
+                T v0[VEC], v1[VEC];
+                ld_chunk<T, VEC>(SV + c_src[k], v0);
+                ld_chunk<T, VEC>(SV + c_src[k] + T2 * PV, v1);
+                DispatchC<T, L, VEC, 0>::run(u, acc[k], v0, v1, tp.lo[2], tp.hi[2], c_out[k] + wrap_off,
+                                             store && c_ok[k]);
+                c_out[k] += s3;
+            }
+        }
+        u = (u + 1 == L) ? 0 : u + 1;
+    }
+    if (closed) {   // flush: planes n3-L+1 .. n3-1 = early partial (already in memory) + what is left in the ring
+        for (int f = 0; f < L - 1; ++f) {
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                if (tid + k * NT < NC_ITEMS) {
+                    T v0[VEC], v1[VEC];
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) { v0[e] = zero_of(T()); v1[e] = zero_of(T()); }
+                    DispatchC<T, L, VEC, 0>::run(u, acc[k], v0, v1, tp.lo[2], tp.hi[2], c_out[k], c_ok[k], true);
+                    c_out[k] += s3;
+                }
+            }
+            u = (u + 1 == L) ? 0 : u + 1;
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Synthesis tile kernel, FULL-ROW variant (8-byte elements, rows of at most NT/2 elements).
+// tools/tile_probe.cu (profiles/r01_tile_probe.md) showed that the memory access pattern of the
+// 32-column tiles is itself the limit of k_rec3_bulk: a copy-only kernel with that geometry reaches
+// 4.4 TB/s, the same copy with full contiguous rows 6.3 TB/s.  Here a CTA owns ALL n1 columns of
+// T2 rows and marches along dim 3:
+//   * staging unit = one (b2 = 0, 1) band pair of one (b1, b3) group: 2 x (T2+L-1) whole rows, which
+//     are CONTIGUOUS in memory -> one cp.async.bulk per band (two when the rows wrap around dim 2),
+//     issued by one thread into an NSTG-deep ring of stages with one mbarrier each; the ring runs
+//     ahead of the arithmetic across group and plane boundaries;
+//   * stage RA (dim 2): thread = column, full tile height, sliding L-row windows (each staged element
+//     is read once); the periodic wrap of dim 1 is materialised as HB + HA pad columns of SU;
+//   * stage RB (dim 1) and RC (dim 3 scatter ring) as in k_rec3_bulk2.
+struct RowsGeo {
+    int pu, pv;            // SU / SV row pitch (elements), odd chunk counts
+    int nstg;              // stages in the ring
+    int stage_elems;       // 2 * (T2+L-1) * n1
+};
+
+template <typename T, int L>
+__host__ __device__ constexpr int rows_pu(int n1) { return (((n1 + L - 1 + 16 / (int)sizeof(T) - 1) / (16 / (int)sizeof(T))) | 1) * (16 / (int)sizeof(T)); }
+template <typename T>
+__host__ __device__ constexpr int rows_pv(int n1) { return ((n1 / (16 / (int)sizeof(T))) | 1) * (16 / (int)sizeof(T)); }
+
+// N1 > 0: row length known at compile time (every shared-memory offset becomes an immediate);
+// N1 == 0: taken from the parameters.
+template <typename T, int L, int T2, int NT, int KC, int N1>
+__global__ void __launch_bounds__(NT, 1)
+k_rec3_rows(const Rec3Params<T> p, const FusedTaps<T, L> tp, const RowsGeo g)
+{
+    constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int HB = L / 2, HA = L / 2 - 1, W2 = T2 + L - 1;
+    constexpr int RH = T2 / 2;                                    // stage-RA rows per item (two items per column)
+    constexpr int R1B = 2 * VEC, NCHB = (R1B + L - 1 + VEC - 1) / VEC;
+    static_assert(sizeof(T) == 8 && T2 % 2 == 0, "8-byte elements, even tile height");
+
+    const int n1 = N1 ? N1 : p.n1;
+    const int pu = N1 ? rows_pu<T, L>(N1) : g.pu;
+    const int pv = N1 ? rows_pv<T>(N1) : g.pv;
+    const int stage_elems = 2 * W2 * n1;
+    const int nstg = g.nstg;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T *STG = reinterpret_cast<T *>(smem_raw);                    // [nstg][2][W2][n1]
+    T *SU = STG + (size_t)nstg * stage_elems;                     // [4][T2][pu]   (q = b1 + 2 b3), dim 2 synthesised, wrap pads
+    T *SV = SU + 4 * T2 * pu;                                     // [2][T2][pv]   (b3), dims 1,2 synthesised
+    uint64_t *bar = reinterpret_cast<uint64_t *>(SV + 2 * T2 * pv);
+
+    const int tid = threadIdx.x;
+    int bid = blockIdx.x;
+    const int t2 = bid % p.tiles2;
+    bid /= p.tiles2;
+    const int chunk = bid % p.nchunks;
+    const int batch = bid / p.nchunks;
+    const int a2 = t2 * T2;
+    const int z0 = chunk * p.zc;
+    const int z1 = min(z0 + p.zc, p.n3);
+    const int n2 = p.n2, n3 = p.n3;
+    const int64_t s3 = p.s3;
+    const int bsel = batch / p.nhyp, bhyp = batch - bsel * p.nhyp;
+    const int64_t boff = (int64_t)bhyp * p.s4;
+
+    const bool closed = (p.nchunks == 1);
+    const int nsteps = closed ? (z1 - z0) : (z1 - z0) + L - 1;
+    const int total = 4 * nsteps;                                 // pair steps
+    const uint32_t stage_bytes = (uint32_t)(stage_elems * sizeof(T));
+
+    // staging: rows a2-HB .. a2-HB+W2-1 (mod n2) of a band plane are one contiguous run (two at the dim-2
+    // wrap): thread 0 issues one or two cp.async.bulk per band.  (One copy per row from many lanes costs
+    // 25 % more instructions over the whole kernel and is slower: profiles/r01_rows_kernel.md.)
+    const int r0 = wrapi(a2 - HB, n2);
+    const int rows0 = min(W2, n2 - r0);
+    int iz = wrapi(z0 - HB, n3);                                  // plane of the next stage to issue
+    int iq = 0;                                                   // group of the next stage to issue
+    auto issue = [&](int stg) {   // stages are issued in order
+        if (tid == 0) {
+            mbar_expect_tx(bar + stg, stage_bytes);
+            const int blo = 8 * bsel + (iq & 1) + 4 * (iq >> 1);
+            T *dst = STG + (size_t)stg * stage_elems;
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {
+                const T *src = p.in[blo + 2 * hb] + boff + (int64_t)iz * s3;
+                T *d = dst + hb * W2 * n1;
+                bulk_g2s(d, src + (int64_t)r0 * n1, (uint32_t)(rows0 * n1 * sizeof(T)), bar + stg);
+                if (rows0 < W2) bulk_g2s(d + rows0 * n1, src, (uint32_t)((W2 - rows0) * n1 * sizeof(T)), bar + stg);
+            }
+        }
+        if (++iq == 4) { iq = 0; if (++iz == n3) iz = 0; }
+    };
+
+    // stage RA: item = (column c, half h of the tile rows)
+    // stage RC: thread owns KC 16-byte output chunks and their L-deep rings of partial sums
+    const int CPR = n1 / VEC, NC_ITEMS = T2 * CPR;
+    int c_src[KC];
+    T *c_out[KC];
+    bool c_ok[KC];
+    T acc[KC][L][VEC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        const int it = tid + k * NT;
+        const int j = (it / CPR) % T2, cp = it - (it / CPR) * CPR;
+        c_src[k] = j * pv + cp * VEC;
+        c_ok[k] = (it < NC_ITEMS) && (a2 + j < n2);
+        c_out[k] = p.out[bsel] + boff + ((int64_t)z0 - (L - 1)) * s3 + (int64_t)(a2 + j) * n1 + cp * VEC;
+#pragma unroll
+        for (int s = 0; s < L; ++s)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[k][s][e] = zero_of(T());
+    }
+
+    if (tid == 0) {
+        for (int i = 0; i < nstg; ++i) mbar_init(bar + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int issued = 0;
+    for (; issued < nstg && issued < total; ++issued) issue(issued);
+
+    const int NA_ITEMS = 2 * n1;
+    const int NB_ITEMS = T2 * (n1 / R1B);
+    int u = 0, stg = 0;
+    uint32_t parity = 0;
+    for (int t = 0; t < nsteps; ++t) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            mbar_wait(bar + stg, parity);
+            // ---- stage RA: dim 2 for group q, sliding windows over both b2 bands
+            {
+                const T *S = STG + (size_t)stg * stage_elems;
+                for (int it = tid; it < NA_ITEMS; it += NT) {
+                    const int h = it / n1, c = it - h * n1;
+                    const T *s0 = S + h * RH * n1 + c;
+                    const T *s1 = s0 + W2 * n1;
+                    T *dst = SU + (q * T2 + h * RH) * pu + HB + c;
+                    const int wl = (c >= n1 - HB) ? -n1 : 0;      // left-pad copy of columns n1-HB .. n1-1
+                    const int wr = (c < HA) ? n1 : 0;             // right-pad copy of columns 0 .. HA-1
+                    // all RH outputs in flight at once: 2 * RH independent FFMA2 chains (two chains stall on the
+                    // FFMA2 latency: "wait" was the top stall reason)
+                    T w0[RH + L - 1], w1[RH + L - 1];
+#pragma unroll
+                    for (int i = 0; i < RH + L - 1; ++i) {
+                        w0[i] = s0[i * n1];
+                        w1[i] = s1[i * n1];
+                    }
+                    T o0[RH], o1[RH];
+#pragma unroll
+                    for (int i = 0; i < RH; ++i) { o0[i] = zero_of(T()); o1[i] = zero_of(T()); }
+#pragma unroll
+                    for (int kk = 0; kk < L; ++kk)
+#pragma unroll
+                        for (int i = 0; i < RH; ++i) {
+                            macp(o0[i], tp.lo[1][kk], w0[i + kk]);
+                            macp(o1[i], tp.hi[1][kk], w1[i + kk]);
+                        }
+#pragma unroll
+                    for (int i = 0; i < RH; ++i) {
+                        o0[i] = add(o0[i], o1[i]);
+                        dst[i * pu] = o0[i];
+                    }
+                    if (wl | wr) {
+                        const int wo = wl ? wl : wr;
+#pragma unroll
+                        for (int i = 0; i < RH; ++i) dst[i * pu + wo] = o0[i];
+                    }
+                }
+            }
+            __syncthreads();   // stage consumed, SU[q] complete
+            if (issued < total) { issue(stg); ++issued; }
+            if (++stg == nstg) { stg = 0; parity ^= 1; }
+
+            // ---- stage RB: dim 1 for b3 = q >> 1 once both of its groups are in SU
+            if (q & 1) {
+                const int b3 = q >> 1;
+                for (int it = tid; it < NB_ITEMS; it += NT) {
+                    const int j = it % T2, cb = it / T2;
+                    const T *ra = SU + (2 * b3 * T2 + j) * pu + cb * R1B;
+                    const T *rb = ra + T2 * pu;
+                    T va[NCHB * VEC], vb[NCHB * VEC];
+#pragma unroll
+                    for (int c = 0; c < NCHB; ++c) {
+                        ld_chunk<T, VEC>(ra + c * VEC, va + c * VEC);
+                        ld_chunk<T, VEC>(rb + c * VEC, vb + c * VEC);
+                    }
+                    T o[R1B], ob[R1B];
+#pragma unroll
+                    for (int i = 0; i < R1B; ++i) { o[i] = zero_of(T()); ob[i] = zero_of(T()); }
+#pragma unroll
+                    for (int kk = 0; kk < L; ++kk)
+#pragma unroll
+                        for (int i = 0; i < R1B; ++i) {
+                            macp(o[i], tp.lo[0][kk], va[i + kk]);
+                            macp(ob[i], tp.hi[0][kk], vb[i + kk]);
+                        }
+#pragma unroll
+                    for (int i = 0; i < R1B; ++i) o[i] = add(o[i], ob[i]);
+                    T *d = SV + (b3 * T2 + j) * pv + cb * R1B;
+#pragma unroll
+                    for (int c = 0; c < R1B / VEC; ++c) st_chunk<T, VEC>(d + c * VEC, o + c * VEC);
+                }
+            }
+        }
+        __syncthreads();   // SV complete
+
+        // ---- stage RC: dim 3 scatter ring
+        const bool store = closed || (t >= L - 1);
+        const int64_t wrap_off = (closed && t < L - 1) ? (int64_t)n3 * s3 : 0;   // early partials of the wrapped planes
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            if (tid + k * NT < NC_ITEMS) {
+                T v0[VEC], v1[VEC];
+                ld_chunk<T, VEC>(SV + c_src[k], v0);
+                ld_chunk<T, VEC>(SV + c_src[k] + T2 * pv, v1);
+                DispatchC<T, L, VEC, 0>::run(u, acc[k], v0, v1, tp.lo[2], tp.hi[2], c_out[k] + wrap_off,
+                                             store && c_ok[k]);
+                c_out[k] += s3;
+            }
+        }
+        u = (u + 1 == L) ? 0 : u + 1;
+    }
+    if (closed) {   // flush: planes n3-L+1 .. n3-1 = early partial (already in memory) + what is left in the ring
+        for (int f = 0; f < L - 1; ++f) {
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                if (tid + k * NT < NC_ITEMS) {
+                    T v0[VEC], v1[VEC];
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) { v0[e] = zero_of(T()); v1[e] = zero_of(T()); }
+                    DispatchC<T, L, VEC, 0>::run(u, acc[k], v0, v1, tp.lo[2], tp.hi[2], c_out[k], c_ok[k], true);
+                    c_out[k] += s3;
+                }
+            }
+            u = (u + 1 == L) ? 0 : u + 1;
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
 // Last-dimension passes of the 4-D path (and the slab-exchange points of the multi-GPU path):
 // one thread owns one 16-byte chunk of the (dim 1..3) hyperplane and marches along dim 4 with an
 // L-deep register ring, so every input hyperplane is read exactly once.
@@ -1194,7 +1674,7 @@ static int pick_zc(int n3, int tiles, int H, int ctas_per_wave)
     return best;
 }
 
-template <typename T, int L, int T2, int NT, int R2, int MINB, int CWSEL = 0>
+template <typename T, int L, int T2, int NT, int R2, int MINB, int CWSEL = 0, int RBM = 1>
 static int launch_dec3_v(nddwt_plan *p, const Dec3Params<T> &base, cudaStream_t s)
 {
     using G = Geo<T, L, T2>;
@@ -1205,7 +1685,7 @@ static int launch_dec3_v(nddwt_plan *p, const Dec3Params<T> &base, cudaStream_t 
     prm.zc = pick_zc(prm.n3, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB);
     prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
     prm.halo_below = (L / 2 - 1);
-    auto kern = k_dec3_fused<T, L, T2, NT, R2, MINB, CWSEL>;
+    auto kern = k_dec3_fused<T, L, T2, NT, R2, MINB, CWSEL, RBM>;
     NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));   // per-device attribute: set on every launch
     const FusedTaps<T, L> tp = make_taps<T, L>(p, false);
     const int64_t grid = (int64_t)prm.tiles1 * prm.tiles2 * prm.nchunks * batches;
@@ -1228,6 +1708,26 @@ static int tuning_variant()
     return v;
 }
 
+// tile-kernel configuration shared by the 3-D path and the 4-D back end (NDDWT_VARIANT % 10 selects
+// tuning variants for the headline case: complex single, db4)
+template <typename T, int L>
+static int launch_dec3_any(nddwt_plan *p, const Dec3Params<T> &prm, cudaStream_t s)
+{
+    if constexpr (L == 8 && sizeof(T) == 8 && Elem<T>::cplx) {
+        switch (tuning_variant() % 10) {
+            case 1: return launch_dec3_v<T, L, 16, 256, 8, 2, 1>(p, prm, s);
+            case 2: return launch_dec3_v<T, L, 16, 256, 4, 2, 1>(p, prm, s);
+            case 3: return launch_dec3_v<T, L, 16, 256, 16, 2, 1>(p, prm, s);
+            case 4: return launch_dec3_v<T, L, 16, 256, 8, 2, 1, 2>(p, prm, s);
+            case 5: return launch_dec3_v<T, L, 16, 192, 16, 2, 1, 2>(p, prm, s);
+            case 6: return launch_dec3_v<T, L, 16, 192, 16, 2, 1, 1>(p, prm, s);
+            case 7: return launch_dec3_v<T, L, 16, 256, 2, 2, 0, 2>(p, prm, s);
+            default: break;
+        }
+    }
+    return launch_dec3_v<T, L, 16, 256, 2, 2>(p, prm, s);
+}
+
 template <typename T, int L>
 static int launch_dec3(nddwt_plan *p, const void *a_in, const LevelIO &io, void *const *out_bands, cudaStream_t s)
 {
@@ -1244,18 +1744,7 @@ static int launch_dec3(nddwt_plan *p, const void *a_in, const LevelIO &io, void 
     prm.n2 = (int)p->dims[1];
     prm.n3 = (int)p->dims[2];
     prm.s3 = p->dims[0] * p->dims[1];
-    if constexpr (L == 8 && sizeof(T) == 8 && Elem<T>::cplx) {   // tuning variants (env NDDWT_VARIANT) for the headline case
-        switch (tuning_variant() % 10) {
-            case 1: return launch_dec3_v<T, L, 12, 256, 4, 2, 0>(p, prm, s);
-            case 2: return launch_dec3_v<T, L, 12, 256, 6, 2, 0>(p, prm, s);
-            case 3: return launch_dec3_v<T, L, 12, 256, 12, 2, 0>(p, prm, s);
-            case 4: return launch_dec3_v<T, L, 12, 256, 2, 2, 0>(p, prm, s);
-            case 5: return launch_dec3_v<T, L, 12, 192, 4, 2, 0>(p, prm, s);
-            case 6: return launch_dec3_v<T, L, 12, 192, 6, 3, 0>(p, prm, s);
-            default: break;
-        }
-    }
-    return launch_dec3_v<T, L, 16, 256, 2, 2>(p, prm, s);
+    return launch_dec3_any<T, L>(p, prm, s);
 }
 
 template <typename T>
@@ -1396,7 +1885,8 @@ static int launch_rec3_bulk(nddwt_plan *p, const Rec3Params<T> &base, cudaStream
         if (cl < 0) { const char *e = getenv("NDDWT_CLUSTER"); cl = e ? atoi(e) : 1; }   // measured: lockstep clusters do not pay (profiles/)
         prm.cl1 = 1;
         prm.cl2 = 1;
-        if (cl == 8 && prm.tiles1 % 2 == 0 && prm.tiles2 % 4 == 0) { prm.cl1 = 2; prm.cl2 = 4; }
+        if (cl == 16 && prm.tiles1 > 1 && prm.tiles1 <= 8) { prm.cl1 = prm.tiles1; prm.cl2 = 1; }   // all dim-1 neighbours of a row block in lockstep
+        else if (cl == 8 && prm.tiles1 % 2 == 0 && prm.tiles2 % 4 == 0) { prm.cl1 = 2; prm.cl2 = 4; }
         else if (cl >= 4 && prm.tiles2 % 4 == 0) { prm.cl1 = 1; prm.cl2 = 4; }
         else if (cl >= 2 && prm.tiles2 % 2 == 0) { prm.cl1 = 1; prm.cl2 = 2; }
     }
@@ -1421,6 +1911,94 @@ static int launch_rec3_bulk(nddwt_plan *p, const Rec3Params<T> &base, cudaStream
     return 0;
 }
 
+template <typename T, int L, int T2, int NT, int MINB>
+static int launch_rec3_bulk2(nddwt_plan *p, const Rec3Params<T> &base, cudaStream_t s)
+{
+    using G = GeoRB2<T, L, T2>;
+    Rec3Params<T> prm = base;
+    prm.tiles1 = (prm.n1 + G::T1 - 1) / G::T1;
+    prm.tiles2 = (prm.n2 + T2 - 1) / T2;
+    const int batches = prm.nhyp * (prm.out[1] ? 2 : 1);
+    prm.zc = pick_zc_rec(prm.n3, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB, true);
+    prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
+    prm.prefetch = 0;
+    prm.cl1 = prm.cl2 = 1;
+    prm.hint = 0;
+    TmaMaps maps;
+    memset(&maps, 0, sizeof maps);
+    if (prm.n1 >= G::W1S && prm.n2 >= G::W2) {
+        const int nb = prm.out[1] ? 16 : 8;
+        bool ok = true;
+        for (int b = 0; b < nb && ok; ++b)
+            ok = encode_band_map(&maps.m[b], prm.in[b], prm.n1, prm.n2, (int64_t)prm.n3 * prm.nhyp, G::W1S, G::W2);
+        if (ok) prm.prefetch = 3;   // kernel flag: tensor maps valid
+    }
+    auto kern = k_rec3_bulk2<T, L, T2, NT, MINB>;
+    NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));   // per-device attribute: set on every launch
+    const FusedTaps<T, L> tp = make_taps<T, L>(p, true);
+    const int64_t grid = (int64_t)prm.tiles1 * prm.tiles2 * prm.nchunks * batches;
+    {
+        LaunchTimer lt(p, KIND_REC3, s);
+        kern<<<(unsigned)grid, NT, G::SMEM, s>>>(prm, tp, maps);
+    }
+    p->launches++;
+    NDDWT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// full-row synthesis kernel: returns -1 when the geometry does not fit (caller falls back)
+template <typename T, int L, int T2, int NT, int KC, int N1>
+static int launch_rec3_rows_n(nddwt_plan *p, const Rec3Params<T> &base, cudaStream_t s)
+{
+    constexpr int VEC = 16 / (int)sizeof(T), W2 = T2 + L - 1;
+    Rec3Params<T> prm = base;
+    const int n1 = prm.n1;
+    if (sizeof(T) != 8 || (N1 && n1 != N1) || n1 % (2 * VEC) != 0 || n1 < 4 * VEC || T2 * (n1 / VEC) > KC * NT ||
+        prm.n2 < W2)
+        return -1;
+    RowsGeo g;
+    g.pu = rows_pu<T, L>(n1);
+    g.pv = rows_pv<T>(n1);
+    g.stage_elems = 2 * W2 * n1;
+    const size_t fixed = ((size_t)4 * T2 * g.pu + (size_t)2 * T2 * g.pv) * sizeof(T) + 64;
+    const size_t stage_bytes = (size_t)g.stage_elems * sizeof(T);
+    const size_t cap = 227 * 1024;
+    if (fixed + 2 * stage_bytes > cap) return -1;
+    g.nstg = (int)std::min<size_t>(4, (cap - fixed) / stage_bytes);
+    const size_t smem = fixed + (size_t)g.nstg * stage_bytes;
+    prm.tiles1 = 1;
+    prm.tiles2 = (prm.n2 + T2 - 1) / T2;
+    const int batches = prm.nhyp * (prm.out[1] ? 2 : 1);
+    {
+        static int min_ctas = -1;   // one CTA per SM: needs many row blocks (4-D batches); tests lower it to reach small shapes
+        if (min_ctas < 0) { const char *e = getenv("NDDWT_ROWS_MIN_CTAS"); min_ctas = e ? atoi(e) : 2 * 148; }
+        if ((int64_t)prm.tiles2 * batches < min_ctas) return -1;
+    }
+    prm.zc = pick_zc_rec(prm.n3, prm.tiles2 * batches, L - 1, 148, true);
+    prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
+    prm.prefetch = 0;
+    prm.cl1 = prm.cl2 = 1;
+    prm.hint = 0;
+    auto kern = k_rec3_rows<T, L, T2, NT, KC, N1>;
+    NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per-device attribute: set on every launch
+    const FusedTaps<T, L> tp = make_taps<T, L>(p, true);
+    const int64_t grid = (int64_t)prm.tiles2 * prm.nchunks * batches;
+    {
+        LaunchTimer lt(p, KIND_REC3, s);
+        kern<<<(unsigned)grid, NT, smem, s>>>(prm, tp, g);
+    }
+    p->launches++;
+    NDDWT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, int L>
+static int launch_rec3_rows(nddwt_plan *p, const Rec3Params<T> &prm, cudaStream_t s)
+{
+    if (prm.n1 == 192) return launch_rec3_rows_n<T, L, 8, 384, 2, 192>(p, prm, s);
+    return launch_rec3_rows_n<T, L, 8, 384, 2, 0>(p, prm, s);
+}
+
 // tile-shape variants of the bulk synthesis kernel (NDDWT_VARIANT / 100 selects; 0 = default)
 template <typename T, int L>
 static int launch_rec3_bulk_any(nddwt_plan *p, const Rec3Params<T> &prm, cudaStream_t s)
@@ -1431,6 +2009,9 @@ static int launch_rec3_bulk_any(nddwt_plan *p, const Rec3Params<T> &prm, cudaStr
             case 2: return launch_rec3_bulk<T, L, 8, 192, 8, 4>(p, prm, s);
             case 3: return launch_rec3_bulk<T, L, 8, 160, 8, 4>(p, prm, s);
             case 4: return launch_rec3_bulk<T, L, 8, 256, 8, 3>(p, prm, s);
+            case 5: return launch_rec3_bulk2<T, L, 16, 192, 2>(p, prm, s);
+            case 6: return launch_rec3_bulk2<T, L, 8, 192, 3>(p, prm, s);
+            case 7: { const int rc = launch_rec3_rows<T, L>(p, prm, s); if (rc >= 0) return rc; break; }
             default: break;
         }
     }
@@ -1613,7 +2194,7 @@ static int dec4_level(nddwt_plan *p, const void *a_in, const LevelIO &io, void *
         for (int b = 0; b < 8; ++b) prm.out[b] = reinterpret_cast<T *>(out_bands[b + (part == 2 ? 0 : 8)]);
         for (int b = 8; b < 16; ++b) prm.out[b] = nullptr;
     }
-    return launch_dec3_v<T, L, 16, 256, 2, 2>(p, prm, s);
+    return launch_dec3_any<T, L>(p, prm, s);
 }
 
 // part: 0 = both halves; 1 = u_lo half (bands 0..7, needs the approximation band); 2 = u_hi half (bands 8..15)
