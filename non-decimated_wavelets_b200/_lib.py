@@ -19,7 +19,7 @@ SYMBOLS = [
     "nddwt_last_error", "nddwt_version", "nddwt_wave_filters", "nddwt_num_bands", "nddwt_infer_level",
     "nddwt_plan_create", "nddwt_plan_create_slab", "nddwt_plan_destroy", "nddwt_plan_set_dilations",
     "nddwt_plan_set_batch", "nddwt_plan_set_kernel_mode", "nddwt_plan_launch_count", "nddwt_plan_last_path",
-    "nddwt_plan_profile", "nddwt_plan_kernel_time",
+    "nddwt_plan_profile", "nddwt_plan_kernel_time", "nddwt_plan_last_synthesis_kernel",
     "nddwt_dec", "nddwt_rec", "nddwt_dec_host", "nddwt_rec_host",
     "nddwt_halo_planes", "nddwt_dec_level_slab", "nddwt_plan_is_separable", "nddwt_dec_level_slab_part", "nddwt_rec_level_slab_stage1_part", "nddwt_rec_level_slab_stage2_scatter", "nddwt_accumulate", "nddwt_rec_level_slab_stage1", "nddwt_rec_level_slab_stage2",
 ]
@@ -60,6 +60,7 @@ def lib():
     L.nddwt_plan_launch_count.argtypes = [vp]
     L.nddwt_plan_launch_count.restype = c.c_int64
     L.nddwt_plan_last_path.argtypes = [vp]
+    L.nddwt_plan_last_synthesis_kernel.argtypes = [vp]
     L.nddwt_plan_profile.argtypes = [vp, c.c_int]
     L.nddwt_plan_kernel_time.argtypes = [vp, c.c_int, dp, c.POINTER(c.c_int64)]
     L.nddwt_dec.argtypes = [vp, vp, vp, c.c_int, vp]
@@ -154,6 +155,11 @@ class Plan:
     @property
     def last_path(self):
         return int(lib().nddwt_plan_last_path(self.handle))
+
+    @property
+    def last_synthesis_kernel(self):
+        """0 none, 1 direct-load tiles, 2 TMA-staged 32-column tiles, 3 the same with full-height windows, 4 full-row tiles."""
+        return int(lib().nddwt_plan_last_synthesis_kernel(self.handle))
 
     def dec(self, x_ptr, c_ptr, level, stream=0):
         check(lib().nddwt_dec(self.handle, x_ptr, c_ptr, level, stream))

@@ -269,6 +269,10 @@ class _NdDwtBase:
     def launches(self):
         return sum(pl.launches for pl in self._plans.values())
 
+    def synthesis_kernels(self):
+        """Synthesis tile kernel each plan of this object launched last (see Plan.last_synthesis_kernel)."""
+        return sorted(set(pl.last_synthesis_kernel for pl in self._plans.values()))
+
 
 class nd_dwt_1D(_NdDwtBase):
     """Functions/nd_dwt_1D.m:63-321."""

@@ -289,6 +289,7 @@ int nddwt_plan_kernel_time(nddwt_plan *p, int kind, double *total_ms, int64_t *c
     return 0;
 }
 int nddwt_plan_last_path(const nddwt_plan *p) { return p ? p->last_path : 0; }
+int nddwt_plan_last_synthesis_kernel(const nddwt_plan *p) { return p ? p->last_rec_kernel : 0; }
 
 int nddwt_dec(nddwt_plan *p, const void *x_dev, void *coeffs_dev, int level, void *stream)
 {

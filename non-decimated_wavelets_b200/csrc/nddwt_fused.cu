@@ -280,23 +280,21 @@ k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
 #pragma unroll
                 for (int j = 0; j < NCH; ++j) ld_chunk<T, VEC>(row + j * VEC, v + j * VEC);
                 T *d0 = SB + b_dst[k];
-                T acc[R1];
+                // lo1 and hi1 together, tap loop outermost: 2 * R1 independent FFMA2 chains
+                T acc[R1], ach[R1];
 #pragma unroll
-                for (int o = 0; o < R1; ++o) {
-                    acc[o] = zero_of(T());
+                for (int o = 0; o < R1; ++o) { acc[o] = zero_of(T()); ach[o] = zero_of(T()); }
 #pragma unroll
-                    for (int j = 0; j < L; ++j) macp(acc[o], tp.lo[0][L - 1 - j], v[o + j]);
-                }
+                for (int j = 0; j < L; ++j)
+#pragma unroll
+                    for (int o = 0; o < R1; ++o) {
+                        macp(acc[o], tp.lo[0][L - 1 - j], v[o + j]);
+                        macp(ach[o], tp.hi[0][L - 1 - j], v[o + j]);
+                    }
 #pragma unroll
                 for (int c = 0; c < R1 / VEC; ++c) st_chunk<T, VEC>(d0 + c * VEC, acc + c * VEC);
 #pragma unroll
-                for (int o = 0; o < R1; ++o) {
-                    acc[o] = zero_of(T());
-#pragma unroll
-                    for (int j = 0; j < L; ++j) macp(acc[o], tp.hi[0][L - 1 - j], v[o + j]);
-                }
-#pragma unroll
-                for (int c = 0; c < R1 / VEC; ++c) st_chunk<T, VEC>(d0 + W2 * PB + c * VEC, acc + c * VEC);
+                for (int c = 0; c < R1 / VEC; ++c) st_chunk<T, VEC>(d0 + W2 * PB + c * VEC, ach + c * VEC);
             }
         }
         __syncthreads();
@@ -1792,6 +1790,7 @@ static int launch_rec3_v(nddwt_plan *p, const Rec3Params<T> &base, cudaStream_t 
         if (pf < 0) { const char *e = getenv("NDDWT_PREFETCH"); pf = e ? atoi(e) : 0; }
         prm.prefetch = pf;
     }
+    p->last_rec_kernel = 1;
     auto kern = k_rec3_fused<T, L, T2, NT, R2, MINB>;
     NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));   // per-device attribute: set on every launch
     const FusedTaps<T, L> tp = make_taps<T, L>(p, true);
@@ -1876,6 +1875,7 @@ static int launch_rec3_bulk(nddwt_plan *p, const Rec3Params<T> &base, cudaStream
             if (ok) prm.prefetch = 3;   // kernel flag: tensor maps valid
         }
     }
+    p->last_rec_kernel = 2;
     auto kern = k_rec3_bulk<T, L, T2, NT, R2, MINB>;
     NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));   // per-device attribute: set on every launch
     const FusedTaps<T, L> tp = make_taps<T, L>(p, true);
@@ -1933,6 +1933,7 @@ static int launch_rec3_bulk2(nddwt_plan *p, const Rec3Params<T> &base, cudaStrea
             ok = encode_band_map(&maps.m[b], prm.in[b], prm.n1, prm.n2, (int64_t)prm.n3 * prm.nhyp, G::W1S, G::W2);
         if (ok) prm.prefetch = 3;   // kernel flag: tensor maps valid
     }
+    p->last_rec_kernel = 3;
     auto kern = k_rec3_bulk2<T, L, T2, NT, MINB>;
     NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));   // per-device attribute: set on every launch
     const FusedTaps<T, L> tp = make_taps<T, L>(p, true);
@@ -1970,8 +1971,9 @@ static int launch_rec3_rows_n(nddwt_plan *p, const Rec3Params<T> &base, cudaStre
     prm.tiles2 = (prm.n2 + T2 - 1) / T2;
     const int batches = prm.nhyp * (prm.out[1] ? 2 : 1);
     {
-        static int min_ctas = -1;   // one CTA per SM: needs many row blocks (4-D batches); tests lower it to reach small shapes
-        if (min_ctas < 0) { const char *e = getenv("NDDWT_ROWS_MIN_CTAS"); min_ctas = e ? atoi(e) : 2 * 148; }
+        // one CTA per SM: needs many row blocks (4-D batches); the tests lower the bound to reach small shapes
+        const char *e = getenv("NDDWT_ROWS_MIN_CTAS");
+        const int min_ctas = e ? atoi(e) : 2 * 148;
         if ((int64_t)prm.tiles2 * batches < min_ctas) return -1;
     }
     prm.zc = pick_zc_rec(prm.n3, prm.tiles2 * batches, L - 1, 148, true);
@@ -1979,6 +1981,7 @@ static int launch_rec3_rows_n(nddwt_plan *p, const Rec3Params<T> &base, cudaStre
     prm.prefetch = 0;
     prm.cl1 = prm.cl2 = 1;
     prm.hint = 0;
+    p->last_rec_kernel = 4;
     auto kern = k_rec3_rows<T, L, T2, NT, KC, N1>;
     NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per-device attribute: set on every launch
     const FusedTaps<T, L> tp = make_taps<T, L>(p, true);
@@ -2011,11 +2014,26 @@ static int launch_rec3_bulk_any(nddwt_plan *p, const Rec3Params<T> &prm, cudaStr
             case 4: return launch_rec3_bulk<T, L, 8, 256, 8, 3>(p, prm, s);
             case 5: return launch_rec3_bulk2<T, L, 16, 192, 2>(p, prm, s);
             case 6: return launch_rec3_bulk2<T, L, 8, 192, 3>(p, prm, s);
-            case 7: { const int rc = launch_rec3_rows<T, L>(p, prm, s); if (rc >= 0) return rc; break; }
             default: break;
         }
     }
     return launch_rec3_bulk<T, L, 16, 320, 8, 2>(p, prm, s);
+}
+
+// synthesis tile kernel choice: full rows (big 4-D batches of 8-byte elements, rows up to 192 elements;
+// NDDWT_VARIANT=9xx switches it off), else TMA-staged 32-column tiles, else direct loads (rows narrower
+// than a staged tile)
+template <typename T, int L>
+static int launch_rec3_any(nddwt_plan *p, const Rec3Params<T> &prm, cudaStream_t s)
+{
+    if constexpr (sizeof(T) == 8) {
+        if (tuning_variant() / 100 != 9) {
+            const int rc = launch_rec3_rows<T, L>(p, prm, s);
+            if (rc >= 0) return rc;
+        }
+    }
+    if (prm.n1 >= GeoRB<T, L, 16>::W1S) return launch_rec3_bulk_any<T, L>(p, prm, s);
+    return launch_rec3_v<T, L, 16, 320, 8, 2>(p, prm, s);
 }
 
 template <typename T, int L>
@@ -2044,8 +2062,7 @@ static int launch_rec3(nddwt_plan *p, const void *const *in_bands, void *a_out, 
             default: break;
         }
     }
-    if (prm.n1 >= GeoRB<T, L, 16>::W1S) return launch_rec3_bulk_any<T, L>(p, prm, s);
-    return launch_rec3_v<T, L, 16, 320, 8, 2>(p, prm, s);
+    return launch_rec3_any<T, L>(p, prm, s);
 }
 
 template <typename T>
@@ -2218,8 +2235,7 @@ static int rec4_stage1(nddwt_plan *p, const void *const *in_bands, T *u_lo, T *u
     prm.s3 = p->dims[0] * p->dims[1];
     prm.s4 = prm.s3 * p->dims[2];
     prm.nhyp = (int)p->dims[3];
-    if (prm.n1 >= GeoRB<T, L, 16>::W1S) return launch_rec3_bulk_any<T, L>(p, prm, s);
-    return launch_rec3_v<T, L, 16, 320, 8, 2>(p, prm, s);
+    return launch_rec3_any<T, L>(p, prm, s);
 }
 
 template <typename T, int L>
