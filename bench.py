@@ -281,7 +281,8 @@ def main():
         step()
     torch.cuda.synchronize()
     plan.profile(False)
-    kinds = ["analysis tile kernel k_dec3_fused", "synthesis tile kernel k_rec3_bulk", "analysis last-dim pass k_dec_last",
+    rec_kernel = {1: "k_rec3_fused", 2: "k_rec3_bulk", 4: "k_rec3_rows"}.get(plan.last_synthesis_kernel, "k_rec3")
+    kinds = ["analysis tile kernel k_dec3_fused", "synthesis tile kernel " + rec_kernel, "analysis last-dim pass k_dec_last",
              "synthesis last-dim pass k_rec_last", "generic separable pass"]
     # algorithmic bytes per launch of each kind: tile kernels move (1 + 2^3) arrays per
     # 3-D problem, i.e. (2 + 16) N e per launch in the 4-D batched form; last-dim passes 3 N e

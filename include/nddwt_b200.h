@@ -102,7 +102,7 @@ NDDWT_API int nddwt_plan_kernel_time(nddwt_plan *plan, int kind, double *total_m
 NDDWT_API int nddwt_plan_last_path(const nddwt_plan *plan);
 /* Which synthesis tile kernel the last fused 3-D/4-D level of this plan launched (tests and profiles):
  * 0 none yet, 1 direct-load tiles (k_rec3_fused), 2 TMA-staged 32-column tiles (k_rec3_bulk),
- * 3 the same with full-height windows (k_rec3_bulk2), 4 full-row tiles (k_rec3_rows). */
+ * 4 full-row tiles (k_rec3_rows). */
 NDDWT_API int nddwt_plan_last_synthesis_kernel(const nddwt_plan *plan);
 
 /* y = dec(x, level)   -- replaces nd_dwt_dec / nd_dwt_dec_1level (mex/nddwt.c:98-139,189-239)

@@ -158,7 +158,7 @@ class Plan:
 
     @property
     def last_synthesis_kernel(self):
-        """0 none, 1 direct-load tiles, 2 TMA-staged 32-column tiles, 3 the same with full-height windows, 4 full-row tiles."""
+        """0 none, 1 direct-load tiles, 2 TMA-staged 32-column tiles, 4 full-row tiles."""
         return int(lib().nddwt_plan_last_synthesis_kernel(self.handle))
 
     def dec(self, x_ptr, c_ptr, level, stream=0):

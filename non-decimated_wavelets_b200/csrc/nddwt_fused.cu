@@ -1006,245 +1006,6 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp, const __grid_consta
 
 
 // ---------------------------------------------------------------------------------------------
-// Synthesis tile kernel, second generation (8-byte elements).  k_rec3_bulk turned out to be bound by
-// the shared-memory data pipe (ncu: ~2000 wavefronts per plane-tile, 22 % of them bank conflicts of
-// the halo-column tail warps), not by HBM or FMA issue.  Same staging (TMA tensor maps / bulk row
-// copies + mbarrier) and the same scatter ring for dim 3, but the two shared-memory stages move
-// fewer bytes:
-//   stage RA: one thread per (q, haloed column) runs the FULL tile height with a sliding L-row
-//             window per band, so every staged element is read exactly once (was (R2+L-1)/R2 times);
-//             column groups are padded to whole 128-byte wavefronts (GP lanes) => no bank conflicts;
-//   stage RB: 4*VEC outputs per item (was 2*VEC): (4*VEC+L-1) inputs per 4*VEC outputs.
-template <typename T, int L, int T2>
-struct GeoRB2 : GeoRB<T, L, T2> {
-    using B = GeoRB<T, L, T2>;
-    static constexpr int LPW = 128 / (int)sizeof(T);                  // lanes per conflict-free wavefront
-    static constexpr int GP = (B::W1 + LPW - 1) / LPW * LPW;          // padded lanes per (q) column group
-    static constexpr int NA_SLOTS = 4 * GP;
-    static constexpr int R1B = 4 * B::VEC;                            // stage-RB outputs per item
-    static constexpr int NCB = B::T1 / R1B;                           // items per row
-    static constexpr int NCHB = (R1B + L - 1 + B::VEC - 1) / B::VEC;  // chunks read per item
-    static constexpr int NB_ITEMS = 2 * NCB * T2;
-    static_assert((NCB - 1) * R1B + NCHB * B::VEC <= B::PU, "stage-RB reads stay inside the SU row pitch");
-};
-
-template <typename T, int L, int T2, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB)
-k_rec3_bulk2(const Rec3Params<T> p, const FusedTaps<T, L> tp, const __grid_constant__ TmaMaps maps)
-{
-    using G = GeoRB2<T, L, T2>;
-    constexpr int VEC = G::VEC, T1 = G::T1, HB = G::HB, HBAL = G::HBAL, SHIFT = G::SHIFT;
-    constexpr int W1 = G::W1, W2 = G::W2, W1S = G::W1S, PU = G::PU, PV = G::PV;
-    constexpr int GP = G::GP, R1B = G::R1B, NCB = G::NCB, NCHB = G::NCHB, NB_ITEMS = G::NB_ITEMS;
-    constexpr int NC_ITEMS = T2 * 16, KC = (NC_ITEMS + NT - 1) / NT;
-    constexpr int NROWS = 8 * W2, KR = (NROWS + NT - 1) / NT;       // staged rows per plane
-    constexpr uint32_t PLANE_BYTES = G::PLANE_BYTES;
-    constexpr int BP = G::BP;
-    static_assert(G::NA_SLOTS <= NT && NB_ITEMS <= NT, "one stage-RA / stage-RB item per thread");
-    static_assert(T2 % 8 == 0, "tile rows");
-
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    T *RAW = reinterpret_cast<T *>(smem_raw);          // [8][W2][W1S]  haloed subband tiles of one plane
-    T *SU = RAW + G::RAW_ELEMS;                         // [4][T2][PU]
-    T *SV = SU + 4 * T2 * PU;                           // [2][T2][PV]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(SV + 2 * T2 * PV);
-
-    const int tid = threadIdx.x;
-    int bid = blockIdx.x;
-    const int t1 = bid % p.tiles1;
-    bid /= p.tiles1;
-    const int t2 = bid % p.tiles2;
-    bid /= p.tiles2;
-    const int chunk = bid % p.nchunks;
-    const int batch = bid / p.nchunks;
-    const int a1 = t1 * T1, a2 = t2 * T2;
-    const int z0 = chunk * p.zc;
-    const int z1 = min(z0 + p.zc, p.n3);
-    const int n1 = p.n1, n2 = p.n2, n3 = p.n3;
-    const int64_t s3 = p.s3;
-    const int bsel = batch / p.nhyp, bhyp = batch - bsel * p.nhyp;
-    const int64_t boff = (int64_t)bhyp * p.s4;
-
-    const bool use_tma = p.prefetch == 3 && (a1 - HBAL >= 0) && (a1 - HBAL + W1S <= n1) && (a2 - HB >= 0) &&
-                         (a2 - HB + W2 <= n2);
-    // ---- hoisted per-thread constants ----
-    // row copies of edge tiles: (band b, haloed row r) -> up to two contiguous segments (periodic wrap along dim 1)
-    const T *r_src[KR];
-    int r_dst[KR];
-    const int r_gc0 = wrapi(a1 - HBAL, n1);
-    const int r_len0 = min(W1S, n1 - r_gc0);
-#pragma unroll
-    for (int k = 0; k < KR; ++k) {
-        constexpr int NW = NT / 32;
-        const int slot = tid + k * NT;
-        const int it = (slot % 32) * NW + (slot / 32) % NW + (slot / NT) * NT;   // round-robin over the warps
-        const int r = it % W2, b = (it < NROWS) ? it / W2 : 0;
-        const int grow = wrapi(a2 - HB + r, n2);
-        r_src[k] = p.in[8 * bsel + b] + boff + (int64_t)grow * n1;
-        r_dst[k] = (it < NROWS) ? b * BP + r * W1S : -1;
-    }
-    // stage RA: thread = (q = b1 + 2 b3, haloed column c), groups padded to GP lanes
-    const int a_q = tid / GP, a_c = tid - a_q * GP;
-    const bool a_on = (tid < G::NA_SLOTS) && (a_c < W1);
-    const int a_qq = a_on ? a_q : 0, a_cc = a_on ? a_c : 0;
-    const int a_src = ((a_qq & 1) + 4 * (a_qq >> 1)) * BP + SHIFT + a_cc;
-    const int a_dst = a_qq * T2 * PU + a_cc;
-    // stage RB: item = (b3, group of R1B outputs cb, row j); lanes run along rows; the upper threads take it
-    const int b_it = tid - (NT - NB_ITEMS);
-    const bool b_on = b_it >= 0;
-    const int b_j = (b_on ? b_it : 0) % T2, b_g = (b_on ? b_it : 0) / T2;
-    const int b_cb = b_g % NCB, b_b3 = b_g / NCB;
-    const int b_src = (2 * b_b3 * T2 + b_j) * PU + b_cb * R1B;
-    const int b_dst = (b_b3 * T2 + b_j) * PV + b_cb * R1B;
-    // stage RC: thread owns KC 16-byte output chunks and their L-deep rings of partial sums
-    int c_src[KC];
-    T *c_out[KC];
-    bool c_ok[KC];
-    T acc[KC][L][VEC];
-#pragma unroll
-    for (int k = 0; k < KC; ++k) {
-        const int it = tid + k * NT;
-        const int cp = it & 15, j = (it >> 4) % T2;
-        c_src[k] = j * PV + cp * VEC;
-        const int g1 = a1 + cp * VEC, g2 = a2 + j;
-        c_ok[k] = (it < NC_ITEMS) && g1 < n1 && g2 < n2;
-        c_out[k] = p.out[bsel] + boff + ((int64_t)z0 - (L - 1)) * s3 + (int64_t)g2 * n1 + g1;
-#pragma unroll
-        for (int s = 0; s < L; ++s)
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) acc[k][s][e] = zero_of(T());
-    }
-
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    auto issue_plane = [&](int zi) {   // caller has already posted expect_tx and synchronised the CTA
-        if (use_tma) {
-            if (tid == 0) {
-                const int zp = bhyp * n3 + zi;
-#pragma unroll
-                for (int b = 0; b < 8; ++b) tma_load_3d(RAW + b * BP, &maps.m[8 * bsel + b], a1 - HBAL, a2 - HB, zp, bar);
-            }
-        } else {
-            const int64_t zoff = (int64_t)zi * s3;
-#pragma unroll
-            for (int k = 0; k < KR; ++k) {
-                if (r_dst[k] >= 0) {
-                    const T *src = r_src[k] + zoff;
-                    T *dst = RAW + r_dst[k];
-                    bulk_g2s(dst, src + r_gc0, (uint32_t)(r_len0 * sizeof(T)), bar);
-                    if (r_len0 < W1S) bulk_g2s(dst + r_len0, src, (uint32_t)((W1S - r_len0) * sizeof(T)), bar);
-                }
-            }
-        }
-    };
-
-    // single chunk = the whole periodic dimension: every coefficient plane is staged exactly once (periodic
-    // closure, see k_rec3_bulk)
-    const bool closed = (p.nchunks == 1);
-    const int nsteps = closed ? (z1 - z0) : (z1 - z0) + L - 1;
-    if (tid == 0) mbar_expect_tx(bar, PLANE_BYTES);
-    __syncthreads();   // the expect_tx must precede every complete_tx of the phase
-    issue_plane(wrapi(z0 - HB, n3));
-
-    int u = 0;
-    uint32_t parity = 0;
-    for (int t = 0; t < nsteps; ++t) {
-        mbar_wait(bar, parity);
-        parity ^= 1;
-
-        // ---- stage RA: dim 2, full tile height, sliding window over the staged rows of both b2 bands
-        if (a_on) {
-            const T *s0 = RAW + a_src;
-            const T *s1 = s0 + 2 * BP;
-            T *dst = SU + a_dst;
-            T w0[L], w1[L];
-#pragma unroll
-            for (int i = 0; i < L - 1; ++i) {
-                w0[i] = s0[i * W1S];
-                w1[i] = s1[i * W1S];
-            }
-#pragma unroll
-            for (int i = 0; i < T2; ++i) {
-                w0[(i + L - 1) % L] = s0[(i + L - 1) * W1S];
-                w1[(i + L - 1) % L] = s1[(i + L - 1) * W1S];
-                T o0 = zero_of(T()), o1 = zero_of(T());
-#pragma unroll
-                for (int kk = 0; kk < L; ++kk) {
-                    macp(o0, tp.lo[1][kk], w0[(i + kk) % L]);
-                    macp(o1, tp.hi[1][kk], w1[(i + kk) % L]);
-                }
-                dst[i * PU] = add(o0, o1);
-            }
-        }
-        __syncthreads();   // RAW fully consumed, SU complete
-
-        // ---- stage the next coefficient plane while RB / RC run
-        if (t + 1 < nsteps) {
-            if (tid == 0) mbar_expect_tx(bar, PLANE_BYTES);
-            issue_plane(wrapi(z0 - HB + t + 1, n3));
-        }
-
-        // ---- stage RB: dim 1
-        if (b_on) {
-            T o[R1B];
-#pragma unroll
-            for (int i = 0; i < R1B; ++i) o[i] = zero_of(T());
-#pragma unroll
-            for (int hb = 0; hb < 2; ++hb) {
-                const T *row = SU + b_src + hb * T2 * PU;
-                const typename TapOf<T>::type *g = hb ? tp.hi[0] : tp.lo[0];
-                T v[NCHB * VEC];
-#pragma unroll
-                for (int j = 0; j < NCHB; ++j) ld_chunk<T, VEC>(row + j * VEC, v + j * VEC);
-#pragma unroll
-                for (int i = 0; i < R1B; ++i)
-#pragma unroll
-                    for (int kk = 0; kk < L; ++kk) macp(o[i], g[kk], v[i + kk]);
-            }
-#pragma unroll
-            for (int j = 0; j < R1B / VEC; ++j) st_chunk<T, VEC>(SV + b_dst + j * VEC, o + j * VEC);
-        }
-        __syncthreads();
-
-        // ---- stage RC: dim 3 scatter ring
-        const bool store = closed || (t >= L - 1);
-        const int64_t wrap_off = (closed && t < L - 1) ? (int64_t)n3 * s3 : 0;   // early partials of the wrapped planes
-#pragma unroll
-        for (int k = 0; k < KC; ++k) {
-            if (tid + k * NT < NC_ITEMS) {
-                T v0[VEC], v1[VEC];
-                ld_chunk<T, VEC>(SV + c_src[k], v0);
-                ld_chunk<T, VEC>(SV + c_src[k] + T2 * PV, v1);
-                DispatchC<T, L, VEC, 0>::run(u, acc[k], v0, v1, tp.lo[2], tp.hi[2], c_out[k] + wrap_off,
-                                             store && c_ok[k]);
-                c_out[k] += s3;
-            }
-        }
-        u = (u + 1 == L) ? 0 : u + 1;
-    }
-    if (closed) {   // flush: planes n3-L+1 .. n3-1 = early partial (already in memory) + what is left in the ring
-        for (int f = 0; f < L - 1; ++f) {
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                if (tid + k * NT < NC_ITEMS) {
-                    T v0[VEC], v1[VEC];
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) { v0[e] = zero_of(T()); v1[e] = zero_of(T()); }
-                    DispatchC<T, L, VEC, 0>::run(u, acc[k], v0, v1, tp.lo[2], tp.hi[2], c_out[k], c_ok[k], true);
-                    c_out[k] += s3;
-                }
-            }
-            u = (u + 1 == L) ? 0 : u + 1;
-        }
-    }
-}
-
-
-// ---------------------------------------------------------------------------------------------
 // Synthesis tile kernel, FULL-ROW variant (8-byte elements, rows of at most NT/2 elements).
 // tools/tile_probe.cu (profiles/r01_tile_probe.md) showed that the memory access pattern of the
 // 32-column tiles is itself the limit of k_rec3_bulk: a copy-only kernel with that geometry reaches
@@ -1256,7 +1017,7 @@ k_rec3_bulk2(const Rec3Params<T> p, const FusedTaps<T, L> tp, const __grid_const
 //     ahead of the arithmetic across group and plane boundaries;
 //   * stage RA (dim 2): thread = column, full tile height, sliding L-row windows (each staged element
 //     is read once); the periodic wrap of dim 1 is materialised as HB + HA pad columns of SU;
-//   * stage RB (dim 1) and RC (dim 3 scatter ring) as in k_rec3_bulk2.
+//   * stage RB (dim 1) and RC (dim 3 scatter ring) as in k_rec3_bulk.
 struct RowsGeo {
     int pu, pv;            // SU / SV row pitch (elements), odd chunk counts
     int nstg;              // stages in the ring
@@ -1713,13 +1474,8 @@ static int launch_dec3_any(nddwt_plan *p, const Dec3Params<T> &prm, cudaStream_t
 {
     if constexpr (L == 8 && sizeof(T) == 8 && Elem<T>::cplx) {
         switch (tuning_variant() % 10) {
-            case 1: return launch_dec3_v<T, L, 16, 256, 8, 2, 1>(p, prm, s);
-            case 2: return launch_dec3_v<T, L, 16, 256, 4, 2, 1>(p, prm, s);
-            case 3: return launch_dec3_v<T, L, 16, 256, 16, 2, 1>(p, prm, s);
-            case 4: return launch_dec3_v<T, L, 16, 256, 8, 2, 1, 2>(p, prm, s);
-            case 5: return launch_dec3_v<T, L, 16, 192, 16, 2, 1, 2>(p, prm, s);
-            case 6: return launch_dec3_v<T, L, 16, 192, 16, 2, 1, 1>(p, prm, s);
-            case 7: return launch_dec3_v<T, L, 16, 256, 2, 2, 0, 2>(p, prm, s);
+            case 1: return launch_dec3_v<T, L, 16, 256, 8, 2, 1>(p, prm, s);        // 8-byte stage-C columns, 8-row runs: 5.4 ms vs 3.6 ms (cfg5)
+            case 5: return launch_dec3_v<T, L, 16, 192, 16, 2, 1, 2>(p, prm, s);    // 192 threads, full-height stage C, wide stage B: 3.9 ms
             default: break;
         }
     }
@@ -1885,8 +1641,7 @@ static int launch_rec3_bulk(nddwt_plan *p, const Rec3Params<T> &base, cudaStream
         if (cl < 0) { const char *e = getenv("NDDWT_CLUSTER"); cl = e ? atoi(e) : 1; }   // measured: lockstep clusters do not pay (profiles/)
         prm.cl1 = 1;
         prm.cl2 = 1;
-        if (cl == 16 && prm.tiles1 > 1 && prm.tiles1 <= 8) { prm.cl1 = prm.tiles1; prm.cl2 = 1; }   // all dim-1 neighbours of a row block in lockstep
-        else if (cl == 8 && prm.tiles1 % 2 == 0 && prm.tiles2 % 4 == 0) { prm.cl1 = 2; prm.cl2 = 4; }
+        if (cl == 8 && prm.tiles1 % 2 == 0 && prm.tiles2 % 4 == 0) { prm.cl1 = 2; prm.cl2 = 4; }
         else if (cl >= 4 && prm.tiles2 % 4 == 0) { prm.cl1 = 1; prm.cl2 = 4; }
         else if (cl >= 2 && prm.tiles2 % 2 == 0) { prm.cl1 = 1; prm.cl2 = 2; }
     }
@@ -1905,42 +1660,6 @@ static int launch_rec3_bulk(nddwt_plan *p, const Rec3Params<T> &base, cudaStream
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         NDDWT_CUDA(cudaLaunchKernelEx(&cfg, kern, prm, tp, maps));
-    }
-    p->launches++;
-    NDDWT_CUDA(cudaGetLastError());
-    return 0;
-}
-
-template <typename T, int L, int T2, int NT, int MINB>
-static int launch_rec3_bulk2(nddwt_plan *p, const Rec3Params<T> &base, cudaStream_t s)
-{
-    using G = GeoRB2<T, L, T2>;
-    Rec3Params<T> prm = base;
-    prm.tiles1 = (prm.n1 + G::T1 - 1) / G::T1;
-    prm.tiles2 = (prm.n2 + T2 - 1) / T2;
-    const int batches = prm.nhyp * (prm.out[1] ? 2 : 1);
-    prm.zc = pick_zc_rec(prm.n3, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB, true);
-    prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
-    prm.prefetch = 0;
-    prm.cl1 = prm.cl2 = 1;
-    prm.hint = 0;
-    TmaMaps maps;
-    memset(&maps, 0, sizeof maps);
-    if (prm.n1 >= G::W1S && prm.n2 >= G::W2) {
-        const int nb = prm.out[1] ? 16 : 8;
-        bool ok = true;
-        for (int b = 0; b < nb && ok; ++b)
-            ok = encode_band_map(&maps.m[b], prm.in[b], prm.n1, prm.n2, (int64_t)prm.n3 * prm.nhyp, G::W1S, G::W2);
-        if (ok) prm.prefetch = 3;   // kernel flag: tensor maps valid
-    }
-    p->last_rec_kernel = 3;
-    auto kern = k_rec3_bulk2<T, L, T2, NT, MINB>;
-    NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));   // per-device attribute: set on every launch
-    const FusedTaps<T, L> tp = make_taps<T, L>(p, true);
-    const int64_t grid = (int64_t)prm.tiles1 * prm.tiles2 * prm.nchunks * batches;
-    {
-        LaunchTimer lt(p, KIND_REC3, s);
-        kern<<<(unsigned)grid, NT, G::SMEM, s>>>(prm, tp, maps);
     }
     p->launches++;
     NDDWT_CUDA(cudaGetLastError());
@@ -2012,8 +1731,6 @@ static int launch_rec3_bulk_any(nddwt_plan *p, const Rec3Params<T> &prm, cudaStr
             case 2: return launch_rec3_bulk<T, L, 8, 192, 8, 4>(p, prm, s);
             case 3: return launch_rec3_bulk<T, L, 8, 160, 8, 4>(p, prm, s);
             case 4: return launch_rec3_bulk<T, L, 8, 256, 8, 3>(p, prm, s);
-            case 5: return launch_rec3_bulk2<T, L, 16, 192, 2>(p, prm, s);
-            case 6: return launch_rec3_bulk2<T, L, 8, 192, 3>(p, prm, s);
             default: break;
         }
     }

@@ -28,7 +28,7 @@ struct nddwt_plan {
     int dil[NDDWT_MAX_LEVELS];
     int kernel_mode = 0;   // 0 auto, 1 generic only
     int last_path = 0;     // 1 fused, 0 generic
-    int last_rec_kernel = 0;   // synthesis tile kernel of the last 3-D/4-D fused level: 1 direct-load, 2 bulk (32-column tiles), 3 bulk2, 4 full rows
+    int last_rec_kernel = 0;   // synthesis tile kernel of the last 3-D/4-D fused level: 1 direct-load, 2 bulk (32-column tiles), 4 full rows
     int64_t launches = 0;
 
     // device scratch owned by the plan (allocated on first use, reused across calls)
