@@ -1690,9 +1690,10 @@ static int launch_rec3_rows_n(nddwt_plan *p, const Rec3Params<T> &base, cudaStre
     prm.tiles2 = (prm.n2 + T2 - 1) / T2;
     const int batches = prm.nhyp * (prm.out[1] ? 2 : 1);
     {
-        // one CTA per SM: needs many row blocks (4-D batches); the tests lower the bound to reach small shapes
+        // one CTA per SM: needs enough row blocks to fill most of the machine once (4-D batches; one rank's
+        // half-level of cfg4 on 8 GPUs is 128 blocks); the tests lower the bound to reach small shapes
         const char *e = getenv("NDDWT_ROWS_MIN_CTAS");
-        const int min_ctas = e ? atoi(e) : 2 * 148;
+        const int min_ctas = e ? atoi(e) : 118;
         if ((int64_t)prm.tiles2 * batches < min_ctas) return -1;
     }
     prm.zc = pick_zc_rec(prm.n3, prm.tiles2 * batches, L - 1, 148, true);
@@ -1718,6 +1719,7 @@ template <typename T, int L>
 static int launch_rec3_rows(nddwt_plan *p, const Rec3Params<T> &prm, cudaStream_t s)
 {
     if (prm.n1 == 192) return launch_rec3_rows_n<T, L, 8, 384, 2, 192>(p, prm, s);
+    if (prm.n1 == 256) return launch_rec3_rows_n<T, L, 8, 512, 2, 256>(p, prm, s);   // 2-stage ring (224 KB), 128-register cap
     return launch_rec3_rows_n<T, L, 8, 384, 2, 0>(p, prm, s);
 }
 

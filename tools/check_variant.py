@@ -8,7 +8,7 @@ import nddwt_b200 as nd
 from oracle import nddwt_oracle as orc
 
 CASES = [((64, 48, 40), "db4", 3), ((32, 32, 24, 16), "db4", 2), ((192, 40, 16, 8), "db4", 1),
-         ((64, 30, 9, 8), "db4", 1), ((128, 17, 12), "db4", 1), ((72, 20, 8, 8), "db4", 1)]
+         ((64, 30, 9, 8), "db4", 1), ((128, 17, 12), "db4", 1), ((256, 24, 10, 8), "db4", 1), ((72, 20, 8, 8), "db4", 1)]
 worst = 0.0
 for sizes, wn, level in CASES:
     x = orc.synth(sizes, np.complex64, 3)
