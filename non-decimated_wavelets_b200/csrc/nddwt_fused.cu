@@ -1690,14 +1690,18 @@ static int launch_rec3_rows_n(nddwt_plan *p, const Rec3Params<T> &base, cudaStre
     prm.tiles2 = (prm.n2 + T2 - 1) / T2;
     const int batches = prm.nhyp * (prm.out[1] ? 2 : 1);
     {
-        // one CTA per SM: needs enough row blocks to fill most of the machine once (4-D batches; one rank's
-        // half-level of cfg4 on 8 GPUs is 128 blocks); the tests lower the bound to reach small shapes
-        const char *e = getenv("NDDWT_ROWS_MIN_CTAS");
-        const int min_ctas = e ? atoi(e) : 118;
-        if ((int64_t)prm.tiles2 * batches < min_ctas) return -1;
-    }
     prm.zc = pick_zc_rec(prm.n3, prm.tiles2 * batches, L - 1, 148, true);
     prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
+    {
+        // one CTA per SM: needs enough row blocks to fill most of the machine once (4-D batches; one rank's
+        // half-level of cfg4 on 8 GPUs is 128 blocks); the tests lower the bound to reach small shapes.
+        // NDDWT_VARIANT=1xxx (untimed so far) also counts the z-chunks, which lets single 3-D volumes in
+        // (256^3: 32 row blocks x 4 chunks of 64+7 planes).
+        const char *e = getenv("NDDWT_ROWS_MIN_CTAS");
+        const int min_ctas = e ? atoi(e) : 118;
+        const int64_t blocks = (int64_t)prm.tiles2 * batches * (tuning_variant() / 1000 == 1 ? prm.nchunks : 1);
+        if (blocks < min_ctas) return -1;
+    }
     prm.prefetch = 0;
     prm.cl1 = prm.cl2 = 1;
     prm.hint = 0;
@@ -1728,7 +1732,7 @@ template <typename T, int L>
 static int launch_rec3_bulk_any(nddwt_plan *p, const Rec3Params<T> &prm, cudaStream_t s)
 {
     if constexpr (L == 8 && sizeof(T) == 8 && Elem<T>::cplx) {
-        switch (tuning_variant() / 100) {
+        switch (tuning_variant() / 100 % 10) {
             case 1: return launch_rec3_bulk<T, L, 32, 640, 8, 1>(p, prm, s);
             case 2: return launch_rec3_bulk<T, L, 8, 192, 8, 4>(p, prm, s);
             case 3: return launch_rec3_bulk<T, L, 8, 160, 8, 4>(p, prm, s);
@@ -1746,7 +1750,7 @@ template <typename T, int L>
 static int launch_rec3_any(nddwt_plan *p, const Rec3Params<T> &prm, cudaStream_t s)
 {
     if constexpr (sizeof(T) == 8) {
-        if (tuning_variant() / 100 != 9) {
+        if (tuning_variant() / 100 % 10 != 9) {
             const int rc = launch_rec3_rows<T, L>(p, prm, s);
             if (rc >= 0) return rc;
         }
@@ -1770,7 +1774,7 @@ static int launch_rec3(nddwt_plan *p, const void *const *in_bands, void *a_out, 
     prm.s4 = 0;
     prm.nhyp = 1;
     if constexpr (L == 8 && sizeof(T) == 8 && Elem<T>::cplx) {
-        switch (tuning_variant() / 10) {
+        switch (tuning_variant() / 10 % 10) {
             case 1: return launch_rec3_v<T, L, 16, 256, 8, 2>(p, prm, s);
             case 2: return launch_rec3_v<T, L, 16, 320, 4, 2>(p, prm, s);
             case 3: return launch_rec3_v<T, L, 16, 256, 4, 2>(p, prm, s);

@@ -65,14 +65,14 @@ __device__ __forceinline__ void st16(T *p, const T *src)
 }
 
 // coeffs: [n1][batch][J+1] column-major => band s of signal b starts at (s * batch + b) * n1
-template <typename T, int L, int TILE, int NT>
+template <typename T, int L, int TILE, int NT, int CPT>
 __global__ void __launch_bounds__(NT)
 k_dec1_cascade(const T *__restrict__ x, T *__restrict__ coeffs, int64_t n1, int64_t batch, int J,
                const Taps1<T, L> tp)
 {
     constexpr int HLs = L / 2 - 1;                 // analysis reads n-(L/2-1) .. n+L/2
     extern __shared__ __align__(16) unsigned char smem1_raw[];
-    const int W0 = (TILE + J * (L - 1) + 2 * (16 / (int)sizeof(T)) + 3) & ~3;   // slack for whole-chunk accesses
+    const int W0 = (TILE + J * (L - 1) + 4 * (16 / (int)sizeof(T)) + 3) & ~3;   // slack for whole-chunk accesses
     T *buf0 = reinterpret_cast<T *>(smem1_raw);
     T *buf1 = buf0 + W0;
     const int tid = threadIdx.x;
@@ -87,27 +87,28 @@ k_dec1_cascade(const T *__restrict__ x, T *__restrict__ coeffs, int64_t n1, int6
         const int Wj = TILE + (J - j) * (L - 1);       // valid outputs of this level
         const int c0 = (J - j) * HLs;                   // buffer index of global t0 at this level
         T *band = coeffs + ((int64_t)(J - j + 1) * batch + b) * n1;     // detail d_j lives in slot J-j+1
-        // each thread produces one 16-byte chunk (VEC consecutive outputs) from NCH chunk loads
-        constexpr int VEC = 16 / (int)sizeof(T), NCH = (VEC + L - 1 + VEC - 1) / VEC;
-        for (int oc = tid; oc * VEC < Wj; oc += NT) {
-            const int o = oc * VEC;
+        // each thread produces CPT 16-byte chunks (R consecutive outputs) from NCH chunk loads; the tap loop is
+        // outermost so that the 2 R accumulations are independent FFMA2 chains (two chains per thread stall on
+        // the FFMA2 latency: profiles/r01_rows_kernel.md)
+        constexpr int VEC = 16 / (int)sizeof(T), R = CPT * VEC, NCH = (R + L - 1 + VEC - 1) / VEC;
+        for (int o = tid * R; o < Wj; o += NT * R) {
             T v[NCH * VEC];
 #pragma unroll
             for (int q = 0; q < NCH; ++q) ld16<T, VEC>(src + o + q * VEC, v + q * VEC);
-            T lo[VEC], hi[VEC];
+            T lo[R], hi[R];
 #pragma unroll
-            for (int r = 0; r < VEC; ++r) {
-                lo[r] = zero_of(T());
-                hi[r] = zero_of(T());
+            for (int r = 0; r < R; ++r) { lo[r] = zero_of(T()); hi[r] = zero_of(T()); }
 #pragma unroll
-                for (int k = 0; k < L; ++k) {
+            for (int k = 0; k < L; ++k)
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
                     mac1(lo[r], tp.lo[k], v[r + (L - 1) - k]);
                     mac1(hi[r], tp.hi[k], v[r + (L - 1) - k]);
                 }
-            }
-            st16<T, VEC>(dst + o, lo);
 #pragma unroll
-            for (int r = 0; r < VEC; ++r) {
+            for (int c = 0; c < CPT; ++c) st16<T, VEC>(dst + o + c * VEC, lo + c * VEC);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
                 const int64_t g = t0 + (o + r - c0);
                 if (o + r >= c0 && o + r < c0 + TILE && g < n1) band[g] = hi[r];
             }
@@ -120,14 +121,14 @@ k_dec1_cascade(const T *__restrict__ x, T *__restrict__ coeffs, int64_t n1, int6
         if (t0 + o < n1) approx[t0 + o] = src[o];
 }
 
-template <typename T, int L, int TILE, int NT>
+template <typename T, int L, int TILE, int NT, int CPT>
 __global__ void __launch_bounds__(NT)
 k_rec1_cascade(const T *__restrict__ coeffs, T *__restrict__ x, int64_t n1, int64_t batch, int J,
                const Taps1<T, L> tp)
 {
     constexpr int HLr = L / 2;                     // synthesis reads n-L/2 .. n+L/2-1
     extern __shared__ __align__(16) unsigned char smem1_raw[];
-    const int WJ = (TILE + J * (L - 1) + 2 * (16 / (int)sizeof(T)) + 3) & ~3;
+    const int WJ = (TILE + J * (L - 1) + 4 * (16 / (int)sizeof(T)) + 3) & ~3;
     T *a0 = reinterpret_cast<T *>(smem1_raw);
     T *a1 = a0 + WJ;
     T *dd = a1 + WJ;
@@ -146,26 +147,29 @@ k_rec1_cascade(const T *__restrict__ coeffs, T *__restrict__ x, int64_t n1, int6
         load_wrapped<T, NT>(dd, dj, t0 - (int64_t)j * HLr, Wj, n1, tid);
         __syncthreads();
         const int Wo = Wj - (L - 1);                   // outputs a_{j-1}
-        constexpr int VEC = 16 / (int)sizeof(T), NCH = (VEC + L - 1 + VEC - 1) / VEC;
-        for (int oc = tid; oc * VEC < Wo; oc += NT) {
-            const int o = oc * VEC;
+        constexpr int VEC = 16 / (int)sizeof(T), R = CPT * VEC, NCH = (R + L - 1 + VEC - 1) / VEC;
+        for (int o = tid * R; o < Wo; o += NT * R) {
             T va[NCH * VEC], vd[NCH * VEC];
 #pragma unroll
             for (int q = 0; q < NCH; ++q) {
                 ld16<T, VEC>(src + o + q * VEC, va + q * VEC);
                 ld16<T, VEC>(dd + o + q * VEC, vd + q * VEC);
             }
-            T acc[VEC];
+            // approximation and detail parts in separate accumulators, tap loop outermost: 2 R independent chains
+            T acc[R], acd[R];
 #pragma unroll
-            for (int r = 0; r < VEC; ++r) {
-                acc[r] = zero_of(T());
+            for (int r = 0; r < R; ++r) { acc[r] = zero_of(T()); acd[r] = zero_of(T()); }
 #pragma unroll
-                for (int k = 0; k < L; ++k) {
+            for (int k = 0; k < L; ++k)
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
                     mac1(acc[r], tp.lo[k], va[r + k]);
-                    mac1(acc[r], tp.hi[k], vd[r + k]);
+                    mac1(acd[r], tp.hi[k], vd[r + k]);
                 }
-            }
-            st16<T, VEC>(dst + o, acc);
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = add(acc[r], acd[r]);
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) st16<T, VEC>(dst + o + c * VEC, acc + c * VEC);
         }
         __syncthreads();
         T *t = src; src = dst; dst = t;
@@ -191,20 +195,20 @@ static Taps1<T, L> make_taps1(const nddwt_plan *p, bool rec)
 template <typename T, int L, int TILE>
 static int launch1(nddwt_plan *p, bool rec, const void *in, void *out, int J, cudaStream_t s)
 {
-    constexpr int NT = 256;
+    constexpr int NT = 256, CPT = 1;   // 16-byte chunks per thread and level (2: measured slower, 7.1 + 10.4 ms vs 5.4 + 9.6 ms on cfg2)
     const int64_t n1 = p->dims[0], batch = p->batch;
-    const size_t W = ((size_t)TILE + (size_t)J * (L - 1) + 2 * (16 / sizeof(T)) + 3) & ~(size_t)3;
+    const size_t W = ((size_t)TILE + (size_t)J * (L - 1) + 4 * (16 / sizeof(T)) + 3) & ~(size_t)3;
     const size_t smem = (rec ? 3 : 2) * W * sizeof(T);
     if (smem > 200 * 1024 || batch > 65535) return 1;
     dim3 grid((unsigned)((n1 + TILE - 1) / TILE), (unsigned)batch);
     if (rec) {
-        auto kern = k_rec1_cascade<T, L, TILE, NT>;
+        auto kern = k_rec1_cascade<T, L, TILE, NT, CPT>;
         NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LaunchTimer lt(p, KIND_REC3, s);
         kern<<<grid, NT, smem, s>>>(reinterpret_cast<const T *>(in), reinterpret_cast<T *>(out), n1, batch, J,
                                     make_taps1<T, L>(p, true));
     } else {
-        auto kern = k_dec1_cascade<T, L, TILE, NT>;
+        auto kern = k_dec1_cascade<T, L, TILE, NT, CPT>;
         NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LaunchTimer lt(p, KIND_DEC3, s);
         kern<<<grid, NT, smem, s>>>(reinterpret_cast<const T *>(in), reinterpret_cast<T *>(out), n1, batch, J,
