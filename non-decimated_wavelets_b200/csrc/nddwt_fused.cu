@@ -1689,7 +1689,6 @@ static int launch_rec3_rows_n(nddwt_plan *p, const Rec3Params<T> &base, cudaStre
     prm.tiles1 = 1;
     prm.tiles2 = (prm.n2 + T2 - 1) / T2;
     const int batches = prm.nhyp * (prm.out[1] ? 2 : 1);
-    {
     prm.zc = pick_zc_rec(prm.n3, prm.tiles2 * batches, L - 1, 148, true);
     prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
     {
