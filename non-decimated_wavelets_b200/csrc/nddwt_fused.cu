@@ -19,6 +19,8 @@
 //     taken from the kernel-parameter constant bank; all index math is hoisted out of the march.
 // k_rec3_bulk   (synthesis tile kernel): TMA-staged (cp.async.bulk.tensor / cp.async.bulk + mbarrier)
 //   haloed subband tiles, stages RA (dim 2) / RB (dim 1) / RC (dim 3, scatter ring of partial sums).
+// k_rec3_rows   (synthesis, full-row tiles for 4-D batches of 8-byte elements): contiguous band-pair stages in an
+//   mbarrier ring, 4.65 -> 3.47 ms per launch on cfg5 (profiles/r01_tile_probe.md, r01_rows_kernel.md).
 // k_rec3_fused  : the same pipeline with direct ld.global.nc loads (rows narrower than a staged tile).
 // k_dec_last / k_rec_last[_scatter] : dim-4 passes of the 4-D path and slab-exchange points (multi-GPU).
 #include <algorithm>
