@@ -20,6 +20,6 @@ for sizes, wn, level in CASES:
     c = orc.synth(ya.shape, np.complex64, 4)
     e = [orc.rel_l2(ya, yb), orc.rel_l2(a.rec(ya), x), orc.rel_l2(a.rec(c), b.rec(c))]
     worst = max(worst, *e)
-    print(sizes, ["%.2e" % v for v in e])
+    print(sizes, ["%.2e" % v for v in e], "synthesis kernel", a.synthesis_kernels())
 print("worst", "%.3e" % worst, "OK" if worst < 2e-6 else "FAIL")
 sys.exit(0 if worst < 2e-6 else 1)
