@@ -1033,14 +1033,17 @@ __host__ __device__ constexpr int rows_pv(int n1) { return ((n1 / (16 / (int)siz
 
 // N1 > 0: row length known at compile time (every shared-memory offset becomes an immediate);
 // N1 == 0: taken from the parameters.
-template <typename T, int L, int T2, int NT, int KC, int N1>
+template <typename T, int L, int T2, int NT, int KC, int N1, int RASPLIT = 2, int RBM = 1>
 __global__ void __launch_bounds__(NT, 1)
 k_rec3_rows(const Rec3Params<T> p, const FusedTaps<T, L> tp, const RowsGeo g)
 {
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr int HB = L / 2, HA = L / 2 - 1, W2 = T2 + L - 1;
-    constexpr int RH = T2 / 2;                                    // stage-RA rows per item (two items per column)
-    constexpr int R1B = 2 * VEC, NCHB = (R1B + L - 1 + VEC - 1) / VEC;
+    // stage-RA rows per item: RASPLIT items per column.  tools/tile_model.py: with TMA writes counted, the kernel
+    // runs at ~85 % of the shared-memory pipe; RASPLIT = 1 and RBM = 2 move 19 % fewer wavefronts but keep only
+    // half of the warps busy in those stages (variants 7xx / 8xx, not yet timed)
+    constexpr int RH = T2 / RASPLIT;
+    constexpr int R1B = 2 * RBM * VEC, NCHB = (R1B + L - 1 + VEC - 1) / VEC;
     static_assert(sizeof(T) == 8 && T2 % 2 == 0, "8-byte elements, even tile height");
 
     const int n1 = N1 ? N1 : p.n1;
@@ -1125,7 +1128,7 @@ k_rec3_rows(const Rec3Params<T> p, const FusedTaps<T, L> tp, const RowsGeo g)
     int issued = 0;
     for (; issued < nstg && issued < total; ++issued) issue(issued);
 
-    const int NA_ITEMS = 2 * n1;
+    const int NA_ITEMS = RASPLIT * n1;
     const int NB_ITEMS = T2 * (n1 / R1B);
     int u = 0, stg = 0;
     uint32_t parity = 0;
@@ -1669,13 +1672,13 @@ static int launch_rec3_bulk(nddwt_plan *p, const Rec3Params<T> &base, cudaStream
 }
 
 // full-row synthesis kernel: returns -1 when the geometry does not fit (caller falls back)
-template <typename T, int L, int T2, int NT, int KC, int N1>
+template <typename T, int L, int T2, int NT, int KC, int N1, int RASPLIT = 2, int RBM = 1>
 static int launch_rec3_rows_n(nddwt_plan *p, const Rec3Params<T> &base, cudaStream_t s)
 {
     constexpr int VEC = 16 / (int)sizeof(T), W2 = T2 + L - 1;
     Rec3Params<T> prm = base;
     const int n1 = prm.n1;
-    if (sizeof(T) != 8 || (N1 && n1 != N1) || n1 % (2 * VEC) != 0 || n1 < 4 * VEC || T2 * (n1 / VEC) > KC * NT ||
+    if (sizeof(T) != 8 || (N1 && n1 != N1) || n1 % (2 * RBM * VEC) != 0 || n1 < 4 * VEC || T2 * (n1 / VEC) > KC * NT ||
         prm.n2 < W2)
         return -1;
     RowsGeo g;
@@ -1707,7 +1710,7 @@ static int launch_rec3_rows_n(nddwt_plan *p, const Rec3Params<T> &base, cudaStre
     prm.cl1 = prm.cl2 = 1;
     prm.hint = 0;
     p->last_rec_kernel = 4;
-    auto kern = k_rec3_rows<T, L, T2, NT, KC, N1>;
+    auto kern = k_rec3_rows<T, L, T2, NT, KC, N1, RASPLIT, RBM>;
     NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per-device attribute: set on every launch
     const FusedTaps<T, L> tp = make_taps<T, L>(p, true);
     const int64_t grid = (int64_t)prm.tiles2 * prm.nchunks * batches;
@@ -1723,6 +1726,11 @@ static int launch_rec3_rows_n(nddwt_plan *p, const Rec3Params<T> &base, cudaStre
 template <typename T, int L>
 static int launch_rec3_rows(nddwt_plan *p, const Rec3Params<T> &prm, cudaStream_t s)
 {
+    if constexpr (L == 8 && Elem<T>::cplx) {   // untimed variants for the headline case (tools/tile_model.py)
+        if (prm.n1 == 192 && tuning_variant() / 100 % 10 == 7) return launch_rec3_rows_n<T, L, 8, 384, 2, 192, 1, 2>(p, prm, s);
+        if (prm.n1 == 192 && tuning_variant() / 100 % 10 == 8) return launch_rec3_rows_n<T, L, 8, 384, 2, 192, 1, 1>(p, prm, s);
+        if (prm.n1 == 192 && tuning_variant() / 100 % 10 == 6) return launch_rec3_rows_n<T, L, 8, 384, 2, 192, 2, 2>(p, prm, s);
+    }
     if (prm.n1 == 192) return launch_rec3_rows_n<T, L, 8, 384, 2, 192>(p, prm, s);
     if (prm.n1 == 256) return launch_rec3_rows_n<T, L, 8, 512, 2, 256>(p, prm, s);   // 2-stage ring (224 KB), 128-register cap
     return launch_rec3_rows_n<T, L, 8, 384, 2, 0>(p, prm, s);
