@@ -1008,7 +1008,8 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp, const __grid_consta
 
 
 // ---------------------------------------------------------------------------------------------
-// Synthesis tile kernel, FULL-ROW variant (8-byte elements, rows of at most NT/2 elements).
+// Synthesis tile kernel, FULL-ROW variant (8-byte elements, rows of at most KC*NT*VEC/T2 elements: 192 with 384
+// threads, 256 with 512).
 // tools/tile_probe.cu (profiles/r01_tile_probe.md) showed that the memory access pattern of the
 // 32-column tiles is itself the limit of k_rec3_bulk: a copy-only kernel with that geometry reaches
 // 4.4 TB/s, the same copy with full contiguous rows 6.3 TB/s.  Here a CTA owns ALL n1 columns of
@@ -1017,9 +1018,11 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp, const __grid_consta
 //     are CONTIGUOUS in memory -> one cp.async.bulk per band (two when the rows wrap around dim 2),
 //     issued by one thread into an NSTG-deep ring of stages with one mbarrier each; the ring runs
 //     ahead of the arithmetic across group and plane boundaries;
-//   * stage RA (dim 2): thread = column, full tile height, sliding L-row windows (each staged element
-//     is read once); the periodic wrap of dim 1 is materialised as HB + HA pad columns of SU;
-//   * stage RB (dim 1) and RC (dim 3 scatter ring) as in k_rec3_bulk.
+//   * stage RA (dim 2): item = (column, half of the tile rows), so that all warps work; the RH outputs of
+//     both bands are 2*RH independent FFMA2 chains (tap loop outermost) over one window of RH+L-1 staged
+//     rows per band; the periodic wrap of dim 1 is materialised as HB + HA pad columns of SU;
+//   * stage RB (dim 1): 2*VEC outputs per item, lo/hi sums as separate chains; stage RC: the dim-3
+//     scatter ring of k_rec3_bulk, two 16-byte chunks per thread.
 struct RowsGeo {
     int pu, pv;            // SU / SV row pitch (elements), odd chunk counts
     int nstg;              // stages in the ring
