@@ -163,7 +163,7 @@ struct DispatchA<T, L, PPT, L> {
                                                const int (&)[PPT], int, const T *) {}
 };
 
-template <typename T, int L, int T2, int NT, int R2, int MINB, int CWSEL = 0, int RBM = 1>
+template <typename T, int L, int T2, int NT, int R2, int MINB, int CWSEL = 0, int RBM = 1, int ZINC = 0>
 __global__ void __launch_bounds__(NT, MINB)
 k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
 {
@@ -267,8 +267,18 @@ k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
 
     T *sa_lo = SA, *sa_hi = SA + W2 * PA;
     int u = 0;
+    // ZINC: the plane to prefetch advances by pointer increments (no integer modulo per plane; stage A spends
+    // ~60 of its 181 instructions per plane and warp on plane addressing and loop control, ncu source view)
+    int zn = (ZINC && !slab) ? wrapi(z0 + 1 + HA, n3) : 0;
+    const T *np = in_base + (int64_t)zn * s3;
     for (int z = z0; z < z1; ++z) {
-        const T *next_plane = (z + 1 < z1) ? plane_ptr(z + 1 + HA) : nullptr;
+        const T *next_plane;
+        if (ZINC && !slab) {
+            next_plane = (z + 1 < z1) ? np : nullptr;
+            if (++zn == n3) { zn = 0; np = in_base; } else np += s3;
+        } else {
+            next_plane = (z + 1 < z1) ? plane_ptr(z + 1 + HA) : nullptr;
+        }
         DispatchA<T, L, PPT, 0>::run(u, ring, tp.lo[2], tp.hi[2], sa_lo, sa_hi, sa_off, g_off, mask, next_plane);
         u = (u + 1 == L) ? 0 : u + 1;
         __syncthreads();
@@ -1441,7 +1451,7 @@ static int pick_zc(int n3, int tiles, int H, int ctas_per_wave)
     return best;
 }
 
-template <typename T, int L, int T2, int NT, int R2, int MINB, int CWSEL = 0, int RBM = 1>
+template <typename T, int L, int T2, int NT, int R2, int MINB, int CWSEL = 0, int RBM = 1, int ZINC = 0>
 static int launch_dec3_v(nddwt_plan *p, const Dec3Params<T> &base, cudaStream_t s)
 {
     using G = Geo<T, L, T2>;
@@ -1452,7 +1462,7 @@ static int launch_dec3_v(nddwt_plan *p, const Dec3Params<T> &base, cudaStream_t 
     prm.zc = pick_zc(prm.n3, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB);
     prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
     prm.halo_below = (L / 2 - 1);
-    auto kern = k_dec3_fused<T, L, T2, NT, R2, MINB, CWSEL, RBM>;
+    auto kern = k_dec3_fused<T, L, T2, NT, R2, MINB, CWSEL, RBM, ZINC>;
     NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));   // per-device attribute: set on every launch
     const FusedTaps<T, L> tp = make_taps<T, L>(p, false);
     const int64_t grid = (int64_t)prm.tiles1 * prm.tiles2 * prm.nchunks * batches;
@@ -1484,6 +1494,7 @@ static int launch_dec3_any(nddwt_plan *p, const Dec3Params<T> &prm, cudaStream_t
         switch (tuning_variant() % 10) {
             case 1: return launch_dec3_v<T, L, 16, 256, 8, 2, 1>(p, prm, s);        // 8-byte stage-C columns, 8-row runs: 5.4 ms vs 3.6 ms (cfg5)
             case 5: return launch_dec3_v<T, L, 16, 192, 16, 2, 1, 2>(p, prm, s);    // 192 threads, full-height stage C, wide stage B: 3.9 ms
+            case 2: return launch_dec3_v<T, L, 16, 256, 2, 2, 0, 1, 1>(p, prm, s);   // default + incremental plane pointer (not yet timed)
             default: break;
         }
     }
