@@ -84,12 +84,16 @@ NDDWT_API int nddwt_plan_set_dilations(nddwt_plan *plan, const int *dil, int nle
 
 /* Extension (the reference has no batch API): the arrays carry one extra trailing
  * dimension of `batch` independent signals/images: x is [dims..., batch], the coefficient stack
- * [dims..., batch, nb].  Batched plans run the generic separable kernels. */
+ * [dims..., batch, nb].  1-D batches run the one-launch cascade kernel; batched 2-D..4-D plans run the
+ * generic separable kernels. */
 NDDWT_API int nddwt_plan_set_batch(nddwt_plan *plan, int64_t batch);
 
 /* Selects the kernel family: 0 = auto (fused kernels where an instantiation exists, generic
  * otherwise), 1 = force the generic separable kernels.  Both run on the GPU. */
 NDDWT_API int nddwt_plan_set_kernel_mode(nddwt_plan *plan, int mode);
+/* Named integer parameters of a plan.  "rows_min_ctas": the full-row synthesis kernel (one CTA per SM) is
+ * chosen when a level offers at least this many CTAs (default 118); the tests set 0 to reach it on small shapes. */
+NDDWT_API int nddwt_plan_set_param(nddwt_plan *plan, const char *name, int64_t value);
 /* Number of kernel launches issued by the plan so far (bench.py's gpu_launches). */
 NDDWT_API int64_t nddwt_plan_launch_count(const nddwt_plan *plan);
 /* Per-kernel timing with CUDA events on the launch stream (bench.py's roofline): switch on, run any

@@ -18,7 +18,7 @@ ERR_ARG, ERR_WAVELET, ERR_SHORT_DIM, ERR_CUDA, ERR_NOMEM, ERR_SIZE = -1, -2, -3,
 SYMBOLS = [
     "nddwt_last_error", "nddwt_version", "nddwt_wave_filters", "nddwt_num_bands", "nddwt_infer_level",
     "nddwt_plan_create", "nddwt_plan_create_slab", "nddwt_plan_destroy", "nddwt_plan_set_dilations",
-    "nddwt_plan_set_batch", "nddwt_plan_set_kernel_mode", "nddwt_plan_launch_count", "nddwt_plan_last_path",
+    "nddwt_plan_set_batch", "nddwt_plan_set_kernel_mode", "nddwt_plan_set_param", "nddwt_plan_launch_count", "nddwt_plan_last_path",
     "nddwt_plan_profile", "nddwt_plan_kernel_time", "nddwt_plan_last_synthesis_kernel",
     "nddwt_dec", "nddwt_rec", "nddwt_dec_host", "nddwt_rec_host",
     "nddwt_halo_planes", "nddwt_dec_level_slab", "nddwt_plan_is_separable", "nddwt_dec_level_slab_part", "nddwt_rec_level_slab_stage1_part", "nddwt_rec_level_slab_stage2_scatter", "nddwt_accumulate", "nddwt_rec_level_slab_stage1", "nddwt_rec_level_slab_stage2",
@@ -57,6 +57,7 @@ def lib():
     L.nddwt_plan_set_dilations.argtypes = [vp, ip, c.c_int]
     L.nddwt_plan_set_batch.argtypes = [vp, c.c_int64]
     L.nddwt_plan_set_kernel_mode.argtypes = [vp, c.c_int]
+    L.nddwt_plan_set_param.argtypes = [vp, c.c_char_p, c.c_int64]
     L.nddwt_plan_launch_count.argtypes = [vp]
     L.nddwt_plan_launch_count.restype = c.c_int64
     L.nddwt_plan_last_path.argtypes = [vp]
@@ -134,6 +135,9 @@ class Plan:
 
     def set_kernel_mode(self, mode):
         check(lib().nddwt_plan_set_kernel_mode(self.handle, int(mode)))
+
+    def set_param(self, name, value):
+        check(lib().nddwt_plan_set_param(self.handle, str(name).encode(), int(value)))
 
     @property
     def launches(self):

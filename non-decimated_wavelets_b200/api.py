@@ -134,6 +134,7 @@ class _NdDwtBase:
         self._plans = {}
         self.dilations = None
         self.kernel_mode = 0
+        self.params = {}
 
     # -- plan cache (the stored-filter object on the device) ---------------------------------
     def _plan(self, is_complex, device_index, batch=1):
@@ -147,8 +148,16 @@ class _NdDwtBase:
             if self.dilations is not None:
                 pl.set_dilations(self.dilations)
             pl.set_kernel_mode(self.kernel_mode)
+            for name, value in self.params.items():
+                pl.set_param(name, value)
             self._plans[key] = pl
         return pl
+
+    def set_param(self, name, value):
+        """Named integer plan parameters (nddwt_plan_set_param), e.g. 'rows_min_ctas'."""
+        self.params[str(name)] = int(value)
+        for pl in self._plans.values():
+            pl.set_param(name, value)
 
     def set_dilations(self, dil):
         """Opt-in a-trous mode (not reference behaviour): dilation per level, finest first."""

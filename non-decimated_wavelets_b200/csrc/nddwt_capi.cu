@@ -256,12 +256,28 @@ int nddwt_plan_set_kernel_mode(nddwt_plan *p, int mode)
     return 0;
 }
 
+int nddwt_plan_set_param(nddwt_plan *p, const char *name, int64_t value)
+{
+    if (!p || !name) { set_error("null argument"); return NDDWT_ERR_ARG; }
+    if (strcmp(name, "rows_min_ctas") == 0) {
+        if (value < 0 || value > (1 << 30)) { set_error("rows_min_ctas out of range"); return NDDWT_ERR_ARG; }
+        p->rows_min_ctas = (int)value;
+        return 0;
+    }
+    set_error(std::string("unknown plan parameter: ") + name);
+    return NDDWT_ERR_ARG;
+}
+
 int64_t nddwt_plan_launch_count(const nddwt_plan *p) { return p ? p->launches : 0; }
 
 int nddwt_plan_profile(nddwt_plan *p, int on)
 {
     if (!p) { set_error("null plan"); return NDDWT_ERR_ARG; }
     p->profiling = on != 0;
+    if (on) {   // a new profiling session starts empty: records nobody read go back to the pool
+        for (size_t i = 0; i < p->timed.size(); ++i) { p->event_pool.push_back(p->timed[i].e0); p->event_pool.push_back(p->timed[i].e1); }
+        p->timed.clear();
+    }
     return 0;
 }
 
@@ -271,19 +287,21 @@ int nddwt_plan_kernel_time(nddwt_plan *p, int kind, double *total_ms, int64_t *c
     NDDWT_CUDA(cudaSetDevice(p->device));
     double tot = 0.0;
     int64_t n = 0;
-    std::vector<nddwt_plan::Timed> keep;
-    for (size_t i = 0; i < p->timed.size(); ++i) {
-        nddwt_plan::Timed &t = p->timed[i];
-        if (t.kind != kind) { keep.push_back(t); continue; }
-        NDDWT_CUDA(cudaEventSynchronize(t.e1));
-        float ms = 0.f;
-        NDDWT_CUDA(cudaEventElapsedTime(&ms, t.e0, t.e1));
-        tot += ms;
-        ++n;
-        p->event_pool.push_back(t.e0);
-        p->event_pool.push_back(t.e1);
-    }
+    // entries of this kind leave `timed` whatever happens (a failed read must not leave an event both in
+    // `timed` and in the pool); their events go back to the pool
+    std::vector<nddwt_plan::Timed> keep, mine;
+    for (size_t i = 0; i < p->timed.size(); ++i) (p->timed[i].kind == kind ? mine : keep).push_back(p->timed[i]);
     p->timed.swap(keep);
+    cudaError_t err = cudaSuccess;
+    for (size_t i = 0; i < mine.size(); ++i) {
+        float ms = 0.f;
+        if (err == cudaSuccess) err = cudaEventSynchronize(mine[i].e1);
+        if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, mine[i].e0, mine[i].e1);
+        if (err == cudaSuccess) { tot += ms; ++n; }
+        p->event_pool.push_back(mine[i].e0);
+        p->event_pool.push_back(mine[i].e1);
+    }
+    if (err != cudaSuccess) return cuda_fail(err, "reading kernel timing events");
     *total_ms = tot;
     *count = n;
     return 0;

@@ -1475,30 +1475,39 @@ static int launch_dec3_v(nddwt_plan *p, const Dec3Params<T> &base, cudaStream_t 
     return 0;
 }
 
+// Experiment switches exist only in tuning builds (make TUNING=1 -> -DNDDWT_TUNING): the release library
+// reads no environment variables.  What each rejected variant measured is in profiles/.
+#ifdef NDDWT_TUNING
+static int tuning_env(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
 static int tuning_variant()
 {
     static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("NDDWT_VARIANT");
-        v = e ? atoi(e) : 0;
-    }
+    if (v < 0) v = tuning_env("NDDWT_VARIANT", 0);
     return v;
 }
+#else
+static constexpr int tuning_env(const char *, int dflt) { return dflt; }
+static constexpr int tuning_variant() { return 0; }
+#endif
 
-// tile-kernel configuration shared by the 3-D path and the 4-D back end (NDDWT_VARIANT % 10 selects
-// tuning variants for the headline case: complex single, db4)
+// tile-kernel configuration shared by the 3-D path and the 4-D back end
 template <typename T, int L>
 static int launch_dec3_any(nddwt_plan *p, const Dec3Params<T> &prm, cudaStream_t s)
 {
+#ifdef NDDWT_TUNING
     if constexpr (L == 8 && sizeof(T) == 8 && Elem<T>::cplx) {
         switch (tuning_variant() % 10) {
-            case 1: return launch_dec3_v<T, L, 16, 256, 8, 2, 1>(p, prm, s);        // 8-byte stage-C columns, 8-row runs: 5.4 ms vs 3.6 ms (cfg5)
-            case 5: return launch_dec3_v<T, L, 16, 192, 16, 2, 1, 2>(p, prm, s);    // 192 threads, full-height stage C, wide stage B: 3.9 ms
-            case 2: return launch_dec3_v<T, L, 16, 256, 2, 2, 0, 1, 1>(p, prm, s);   // default + incremental plane pointer (not yet timed)
+            case 1: return launch_dec3_v<T, L, 16, 256, 2, 2>(p, prm, s);   // plane pointer by integer modulo (round-1 default): 3.74 ms vs 3.53 ms (cfg5)
             default: break;
         }
     }
-    return launch_dec3_v<T, L, 16, 256, 2, 2>(p, prm, s);
+#endif
+    // incremental plane pointer (ZINC): no integer modulo per plane in stage A
+    return launch_dec3_v<T, L, 16, 256, 2, 2, 0, 1, 1>(p, prm, s);
 }
 
 template <typename T, int L>
@@ -1560,11 +1569,7 @@ static int launch_rec3_v(nddwt_plan *p, const Rec3Params<T> &base, cudaStream_t 
     const int batches = prm.nhyp * (prm.out[1] ? 2 : 1);
     prm.zc = pick_zc_rec(prm.n3, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB);
     prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
-    {
-        static int pf = -1;
-        if (pf < 0) { const char *e = getenv("NDDWT_PREFETCH"); pf = e ? atoi(e) : 0; }
-        prm.prefetch = pf;
-    }
+    prm.prefetch = tuning_env("NDDWT_PREFETCH", 0);   // prefetch.global.L1/L2 of the next plane: no gain (profiles/)
     p->last_rec_kernel = 1;
     auto kern = k_rec3_fused<T, L, T2, NT, R2, MINB>;
     NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));   // per-device attribute: set on every launch
@@ -1600,8 +1605,7 @@ static EncodeTiledFn encode_fn()
 
 static CUtensorMapL2promotion l2_promotion()
 {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("NDDWT_L2PROMO"); v = e ? atoi(e) : 0; }
+    const int v = tuning_env("NDDWT_L2PROMO", 0);   // 128B / 256B promotion: no effect (profiles/)
     return v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
                                                                : CU_TENSOR_MAP_L2_PROMOTION_NONE;
 }
@@ -1632,16 +1636,11 @@ static int launch_rec3_bulk(nddwt_plan *p, const Rec3Params<T> &base, cudaStream
     prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
     prm.prefetch = 0;
     prm.cl1 = prm.cl2 = 1;
-    {
-        static int hint = -1;
-        if (hint < 0) { const char *e = getenv("NDDWT_L2HINT"); hint = e ? atoi(e) : 0; }
-        prm.hint = hint;
-    }
+    prm.hint = tuning_env("NDDWT_L2HINT", 0);         // evict_last hints on the staged tiles: no effect (profiles/)
     TmaMaps maps;
     memset(&maps, 0, sizeof maps);
     {
-        static int use = -1;
-        if (use < 0) { const char *e = getenv("NDDWT_TMA"); use = e ? atoi(e) : 1; }
+        const int use = tuning_env("NDDWT_TMA", 1);
         if (use && sizeof(T) == 8 && prm.n1 >= G::W1S && prm.n2 >= G::W2) {
             const int nb = prm.out[1] ? 16 : 8;
             bool ok = true;
@@ -1656,8 +1655,7 @@ static int launch_rec3_bulk(nddwt_plan *p, const Rec3Params<T> &base, cudaStream
     const FusedTaps<T, L> tp = make_taps<T, L>(p, true);
     const int64_t grid = (int64_t)prm.tiles1 * prm.tiles2 * prm.nchunks * batches;
     {
-        static int cl = -1;
-        if (cl < 0) { const char *e = getenv("NDDWT_CLUSTER"); cl = e ? atoi(e) : 1; }   // measured: lockstep clusters do not pay (profiles/)
+        const int cl = tuning_env("NDDWT_CLUSTER", 1);   // measured: lockstep clusters do not pay (profiles/)
         prm.cl1 = 1;
         prm.cl2 = 1;
         if (cl == 8 && prm.tiles1 % 2 == 0 && prm.tiles2 % 4 == 0) { prm.cl1 = 2; prm.cl2 = 4; }
@@ -1711,14 +1709,12 @@ static int launch_rec3_rows_n(nddwt_plan *p, const Rec3Params<T> &base, cudaStre
     prm.zc = pick_zc_rec(prm.n3, prm.tiles2 * batches, L - 1, 148, true);
     prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
     {
-        // one CTA per SM: needs enough row blocks to fill most of the machine once (4-D batches; one rank's
-        // half-level of cfg4 on 8 GPUs is 128 blocks); the tests lower the bound to reach small shapes.
-        // NDDWT_VARIANT=1xxx (untimed so far) also counts the z-chunks, which lets single 3-D volumes in
-        // (256^3: 32 row blocks x 4 chunks of 64+7 planes).
-        const char *e = getenv("NDDWT_ROWS_MIN_CTAS");
-        const int min_ctas = e ? atoi(e) : 118;
-        const int64_t blocks = (int64_t)prm.tiles2 * batches * (tuning_variant() / 1000 == 1 ? prm.nchunks : 1);
-        if (blocks < min_ctas) return -1;
+        // one CTA per SM: needs enough CTAs (row blocks x z-chunks x batches) to fill most of the machine once
+        // (one rank's half-level of cfg4 on 8 GPUs is 128 blocks; a 256^3 volume is 32 row blocks x 4 chunks of
+        // 64+7 planes: 1.37 -> 0.87 ms for the three synthesis levels of cfg3).  Tests lower the bound through
+        // nddwt_plan_set_param("rows_min_ctas") to reach small shapes.
+        const int64_t blocks = (int64_t)prm.tiles2 * batches * prm.nchunks;
+        if (blocks < p->rows_min_ctas) return -1;
     }
     prm.prefetch = 0;
     prm.cl1 = prm.cl2 = 1;
@@ -1740,20 +1736,18 @@ static int launch_rec3_rows_n(nddwt_plan *p, const Rec3Params<T> &base, cudaStre
 template <typename T, int L>
 static int launch_rec3_rows(nddwt_plan *p, const Rec3Params<T> &prm, cudaStream_t s)
 {
-    if constexpr (L == 8 && Elem<T>::cplx) {   // untimed variants for the headline case (tools/tile_model.py)
-        if (prm.n1 == 192 && tuning_variant() / 100 % 10 == 7) return launch_rec3_rows_n<T, L, 8, 384, 2, 192, 1, 2>(p, prm, s);
-        if (prm.n1 == 192 && tuning_variant() / 100 % 10 == 8) return launch_rec3_rows_n<T, L, 8, 384, 2, 192, 1, 1>(p, prm, s);
-        if (prm.n1 == 192 && tuning_variant() / 100 % 10 == 6) return launch_rec3_rows_n<T, L, 8, 384, 2, 192, 2, 2>(p, prm, s);
-    }
+    // RASPLIT = 1 / RBM = 2 (19 % fewer shared-memory wavefronts, but half of the warps idle in those stages)
+    // measured slower in round 2: 3.87 / 3.70 / 3.93 ms vs 3.64 ms (profiles/r02_variants.md)
     if (prm.n1 == 192) return launch_rec3_rows_n<T, L, 8, 384, 2, 192>(p, prm, s);
     if (prm.n1 == 256) return launch_rec3_rows_n<T, L, 8, 512, 2, 256>(p, prm, s);   // 2-stage ring (224 KB), 128-register cap
     return launch_rec3_rows_n<T, L, 8, 384, 2, 0>(p, prm, s);
 }
 
-// tile-shape variants of the bulk synthesis kernel (NDDWT_VARIANT / 100 selects; 0 = default)
+// tile-shape variants of the bulk synthesis kernel (tuning builds: NDDWT_VARIANT / 100 selects; 0 = default)
 template <typename T, int L>
 static int launch_rec3_bulk_any(nddwt_plan *p, const Rec3Params<T> &prm, cudaStream_t s)
 {
+#ifdef NDDWT_TUNING
     if constexpr (L == 8 && sizeof(T) == 8 && Elem<T>::cplx) {
         switch (tuning_variant() / 100 % 10) {
             case 1: return launch_rec3_bulk<T, L, 32, 640, 8, 1>(p, prm, s);
@@ -1763,12 +1757,13 @@ static int launch_rec3_bulk_any(nddwt_plan *p, const Rec3Params<T> &prm, cudaStr
             default: break;
         }
     }
+#endif
     return launch_rec3_bulk<T, L, 16, 320, 8, 2>(p, prm, s);
 }
 
-// synthesis tile kernel choice: full rows (big 4-D batches of 8-byte elements, rows up to 192 elements;
-// NDDWT_VARIANT=9xx switches it off), else TMA-staged 32-column tiles, else direct loads (rows narrower
-// than a staged tile)
+// synthesis tile kernel choice: full rows (8-byte elements, rows up to 256 elements, enough CTAs to fill the
+// machine; tuning builds: NDDWT_VARIANT=9xx switches it off), else TMA-staged 32-column tiles, else direct
+// loads (rows narrower than a staged tile)
 template <typename T, int L>
 static int launch_rec3_any(nddwt_plan *p, const Rec3Params<T> &prm, cudaStream_t s)
 {
@@ -1796,6 +1791,7 @@ static int launch_rec3(nddwt_plan *p, const void *const *in_bands, void *a_out, 
     prm.s3 = p->dims[0] * p->dims[1];
     prm.s4 = 0;
     prm.nhyp = 1;
+#ifdef NDDWT_TUNING
     if constexpr (L == 8 && sizeof(T) == 8 && Elem<T>::cplx) {
         switch (tuning_variant() / 10 % 10) {
             case 1: return launch_rec3_v<T, L, 16, 256, 8, 2>(p, prm, s);
@@ -1808,6 +1804,7 @@ static int launch_rec3(nddwt_plan *p, const void *const *in_bands, void *a_out, 
             default: break;
         }
     }
+#endif
     return launch_rec3_any<T, L>(p, prm, s);
 }
 
@@ -2043,10 +2040,22 @@ static int dispatch_rec_last_scatter(nddwt_plan *p, const void *u_lo, const void
                                                    reinterpret_cast<T *>(over_hi), s)));
 }
 
+// int-range guards: the tile kernels index planes with ints and put every CTA in grid.x
+static bool fused_ranges_ok(const nddwt_plan *p)
+{
+    if (p->dims[0] * p->dims[1] >= (int64_t)1 << 30) return false;
+    if (p->dims[2] > (1 << 24)) return false;
+    if (p->ndims == 4 && p->dims[3] > (1 << 20)) return false;
+    // CTAs: tiles x z-chunks x (2 x hyperplanes) must fit grid.x
+    const int64_t tiles = ((p->dims[0] + 31) / 32) * ((p->dims[1] + 7) / 8);
+    const int64_t batches = p->ndims == 4 ? 2 * p->dims[3] : 1;
+    return tiles * ((p->dims[2] + 3) / 4) * batches < (int64_t)0x7fffffff;
+}
+
 static bool fused_geometry_ok(const nddwt_plan *p)
 {
     if (p->ndims < 3 || p->batch != 1) return false;
-    if (p->dims[0] * p->dims[1] >= (int64_t)1 << 30) return false;
+    if (!fused_ranges_ok(p)) return false;
     if (p->dims[0] < p->L[0] || p->dims[1] < p->L[1]) return false;
     if (p->dims[0] % (16 / (int64_t)p->esize) != 0) return false;   // 16-byte rows (vector stores, bulk copies)
     return true;
@@ -2119,7 +2128,7 @@ int fused_dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io,
 {
     if (dil != 1 || !uniform_taps(p)) return 1;
     if (p->ndims == 3) {
-        if (p->dims[0] * p->dims[1] >= (int64_t)1 << 30) return 1;
+        if (!fused_ranges_ok(p)) return 1;
         if (p->dims[0] < p->L[0] || p->dims[1] < p->L[1]) return 1;
         if (p->dims[0] % (16 / (int64_t)p->esize) != 0) return 1;   // 16-byte row alignment for the vector stores
         switch (p->dtype) {
@@ -2139,7 +2148,7 @@ int fused_rec_level(nddwt_plan *p, int dil, const void *const *in_bands, void *a
 {
     if (dil != 1 || !uniform_taps(p)) return 1;
     if (p->ndims == 3) {
-        if (p->dims[0] * p->dims[1] >= (int64_t)1 << 30) return 1;
+        if (!fused_ranges_ok(p)) return 1;
         if (p->dims[0] < p->L[0] || p->dims[1] < p->L[1]) return 1;
         if (p->dims[0] % (16 / (int64_t)p->esize) != 0) return 1;
         switch (p->dtype) {

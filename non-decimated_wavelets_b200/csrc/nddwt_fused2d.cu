@@ -203,6 +203,8 @@ static bool ok2d(const nddwt_plan *p, int dil, const LevelIO *io)
 {
     if (dil != 1 || p->ndims != 2 || p->batch != 1 || p->L[0] != p->L[1]) return false;
     if (io && (io->halo_lo || io->halo_hi)) return false;      // slabs of 2-D arrays use the generic kernels
+    // launch geometry: dims are ints in the kernels, grid.y = ceil(n2 / 16) must stay <= 65535
+    if (p->dims[0] > 0x7fffffff - 64 || p->dims[1] > (int64_t)65535 * 16) return false;
     return p->dims[0] * p->dims[1] < ((int64_t)1 << 40);
 }
 

@@ -30,6 +30,7 @@ struct nddwt_plan {
     int last_path = 0;     // 1 fused, 0 generic
     int last_rec_kernel = 0;   // synthesis tile kernel of the last 3-D/4-D fused level: 1 direct-load, 2 bulk (32-column tiles), 4 full rows
     int64_t launches = 0;
+    int rows_min_ctas = 118;   // full-row synthesis kernel needs at least this many CTAs (nddwt_plan_set_param)
 
     // device scratch owned by the plan (allocated on first use, reused across calls)
     void *approx[2] = {nullptr, nullptr};      // ping-pong intermediate approximation bands

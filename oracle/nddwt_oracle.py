@@ -10,7 +10,7 @@ Pinning status: the reference holds NO golden vectors or known-answer tests for 
 The oracle is therefore pinned by
   (1) `oracle/_ref` -- the reference's own `mex/nddwt.c`, compiled from where it lies under
       /root/reference and linked against a stand-in for the five FFTW symbols it calls
-      (oracle/fftw_standin.c); `tests/test_oracle_vs_ref.py` feeds both the same FFT-domain
+      (oracle/fftw_standin.c); `tests/test_oracle.py` feeds both the same FFT-domain
       inputs and compares (runs in the build container, where /root/reference exists);
   (2) the properties the reference's scripts print: perfect reconstruction, energy
       preservation with pres_l2_norm, mat-path == mex-path, Haar == db1;
