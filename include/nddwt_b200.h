@@ -178,6 +178,56 @@ NDDWT_API int nddwt_rec_level_slab_stage2_scatter(nddwt_plan *plan, int level_in
 /* dst[i] += src[i] for nelem elements of the plan's dtype (device pointers). */
 NDDWT_API int nddwt_accumulate(nddwt_plan *plan, void *dst, const void *src, int64_t nelem, void *stream);
 
+/* ---- multi-GPU plan: the plan owns the peer mapping and the halo exchange --------
+ * The array is split in contiguous slabs along the LAST dimension (at most +-1 plane ragged); rank r holds
+ * its planes of x ([dims[0..d-2], count_r]) and of every subband (coefficient slab [dims[0..d-2], count_r, nb],
+ * band = slowest dim, same band order as nddwt_dec).  Per level the ranks push the halo planes their
+ * neighbours need straight into peer memory with copy-engine peer copies over NVLink (analysis: L/2-1 planes
+ * below, L/2 above of the approximation band; synthesis: the L-1 overhang planes of partial sums of the
+ * scatter-form last-dim pass), overlapped with the tile pass that does not feed the exchange.  No NCCL.
+ *
+ * (1) one process drives all GPUs (C / MATLAB callers): */
+typedef struct nddwt_mplan nddwt_mplan;
+NDDWT_API int nddwt_mplan_create(nddwt_mplan **mplan, int ndims, const int64_t *dims, const char *const *wnames,
+                                 int dtype, int pres_l2_norm, int ngpus, const int *devices /* NULL: 0..ngpus-1 */);
+/* (2) one process per GPU (torchrun): create the rank's plan, all-gather the export blobs
+ *     (nddwt_mplan_export_size() bytes each, rank order) with any host-side transport, import them.  The
+ *     blobs carry CUDA IPC handles of the halo inboxes: all ranks must run on the same node. */
+NDDWT_API int nddwt_mplan_create_rank(nddwt_mplan **mplan, int ndims, const int64_t *dims, const char *const *wnames,
+                                      int dtype, int pres_l2_norm, int rank, int world, int device);
+NDDWT_API int64_t nddwt_mplan_export_size(void);
+NDDWT_API int nddwt_mplan_export(nddwt_mplan *mplan, void *blob);
+NDDWT_API int nddwt_mplan_import(nddwt_mplan *mplan, const void *blobs);
+NDDWT_API int nddwt_mplan_destroy(nddwt_mplan *mplan);
+
+NDDWT_API int nddwt_mplan_world(const nddwt_mplan *mplan);
+NDDWT_API int nddwt_mplan_num_local(const nddwt_mplan *mplan);   /* ranks this process drives: ngpus or 1 */
+NDDWT_API int nddwt_mplan_slab(const nddwt_mplan *mplan, int rank, int64_t *start, int64_t *count);
+NDDWT_API int nddwt_mplan_is_separable(const nddwt_mplan *mplan); /* 1: overlapped scatter schedule (fused 4-D path) */
+NDDWT_API int nddwt_mplan_set_dilations(nddwt_mplan *mplan, const int *dil, int nlevels);  /* a-trous: halos (L-1)*dil */
+NDDWT_API int nddwt_mplan_set_kernel_mode(nddwt_mplan *mplan, int mode);
+NDDWT_API int nddwt_mplan_set_param(nddwt_mplan *mplan, const char *name, int64_t value);
+
+/* y = dec(x, level) / x = rec(y) on slabs.  x_slabs / coeff_slabs: one DEVICE pointer per local rank (in
+ * rank order) on that rank's device; streams: one cudaStream_t per local rank, or NULL for plan-owned
+ * streams.  Asynchronous; nddwt_mplan_sync waits for every local rank.  In the one-process-per-GPU form
+ * every rank must make the same calls in the same order. */
+NDDWT_API int nddwt_mplan_dec(nddwt_mplan *mplan, const void *const *x_slabs, void *const *coeff_slabs, int level,
+                              void *const *streams);
+NDDWT_API int nddwt_mplan_rec(nddwt_mplan *mplan, const void *const *coeff_slabs, void *const *x_slabs, int level,
+                              void *const *streams);
+NDDWT_API int nddwt_mplan_sync(nddwt_mplan *mplan);
+NDDWT_API int64_t nddwt_mplan_launch_count(const nddwt_mplan *mplan);
+NDDWT_API int64_t nddwt_mplan_halo_bytes(const nddwt_mplan *mplan);     /* bytes pushed to peers so far (local ranks) */
+NDDWT_API int nddwt_mplan_wait_timeouts(const nddwt_mplan *mplan);      /* peer flag waits that gave up (0 when healthy) */
+
+/* Host-only routing query (no device): the planes rank `rank` of `world` needs below (which = 0) or above
+ * (which = 1) its slab for a halo of (below, above) planes of a periodic last dimension of n_last planes, as
+ * runs {owner rank, first local plane, count, first halo slot} written to runs4[4 * k ..]; returns the
+ * number of runs (halos wider than a slab come from several ranks, possibly from the rank itself). */
+NDDWT_API int nddwt_slab_route(int64_t n_last, int world, int rank, int which, int64_t below, int64_t above,
+                               int64_t *runs4, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,11 @@ SYMBOLS = [
     "nddwt_plan_set_batch", "nddwt_plan_set_kernel_mode", "nddwt_plan_set_param", "nddwt_plan_launch_count", "nddwt_plan_last_path",
     "nddwt_plan_profile", "nddwt_plan_kernel_time", "nddwt_plan_last_synthesis_kernel",
     "nddwt_dec", "nddwt_rec", "nddwt_dec_host", "nddwt_rec_host",
+    "nddwt_mplan_create", "nddwt_mplan_create_rank", "nddwt_mplan_export_size", "nddwt_mplan_export",
+    "nddwt_mplan_import", "nddwt_mplan_destroy", "nddwt_mplan_world", "nddwt_mplan_num_local", "nddwt_mplan_slab",
+    "nddwt_mplan_is_separable", "nddwt_mplan_set_dilations", "nddwt_mplan_set_kernel_mode", "nddwt_mplan_set_param",
+    "nddwt_mplan_dec", "nddwt_mplan_rec", "nddwt_mplan_sync", "nddwt_mplan_launch_count", "nddwt_mplan_halo_bytes",
+    "nddwt_mplan_wait_timeouts", "nddwt_slab_route",
     "nddwt_halo_planes", "nddwt_dec_level_slab", "nddwt_plan_is_separable", "nddwt_dec_level_slab_part", "nddwt_rec_level_slab_stage1_part", "nddwt_rec_level_slab_stage2_scatter", "nddwt_accumulate", "nddwt_rec_level_slab_stage1", "nddwt_rec_level_slab_stage2",
 ]
 
@@ -77,8 +82,41 @@ def lib():
     L.nddwt_accumulate.argtypes = [vp, vp, vp, c.c_int64, vp]
     L.nddwt_rec_level_slab_stage1.argtypes = [vp, c.c_int, c.POINTER(vp), vp, vp, vp]
     L.nddwt_rec_level_slab_stage2.argtypes = [vp, c.c_int, vp, vp, vp, vp, vp, vp]
+    L.nddwt_mplan_create.argtypes = [c.POINTER(vp), c.c_int, i64p, c.POINTER(c.c_char_p), c.c_int, c.c_int, c.c_int, ip]
+    L.nddwt_mplan_create_rank.argtypes = [c.POINTER(vp), c.c_int, i64p, c.POINTER(c.c_char_p), c.c_int, c.c_int,
+                                          c.c_int, c.c_int, c.c_int]
+    L.nddwt_mplan_export_size.restype = c.c_int64
+    L.nddwt_mplan_export.argtypes = [vp, vp]
+    L.nddwt_mplan_import.argtypes = [vp, vp]
+    L.nddwt_mplan_destroy.argtypes = [vp]
+    L.nddwt_mplan_world.argtypes = [vp]
+    L.nddwt_mplan_num_local.argtypes = [vp]
+    L.nddwt_mplan_slab.argtypes = [vp, c.c_int, i64p, i64p]
+    L.nddwt_mplan_is_separable.argtypes = [vp]
+    L.nddwt_mplan_set_dilations.argtypes = [vp, ip, c.c_int]
+    L.nddwt_mplan_set_kernel_mode.argtypes = [vp, c.c_int]
+    L.nddwt_mplan_set_param.argtypes = [vp, c.c_char_p, c.c_int64]
+    L.nddwt_mplan_dec.argtypes = [vp, c.POINTER(vp), c.POINTER(vp), c.c_int, c.POINTER(vp)]
+    L.nddwt_mplan_rec.argtypes = [vp, c.POINTER(vp), c.POINTER(vp), c.c_int, c.POINTER(vp)]
+    L.nddwt_mplan_sync.argtypes = [vp]
+    L.nddwt_mplan_launch_count.argtypes = [vp]
+    L.nddwt_mplan_launch_count.restype = c.c_int64
+    L.nddwt_mplan_halo_bytes.argtypes = [vp]
+    L.nddwt_mplan_halo_bytes.restype = c.c_int64
+    L.nddwt_mplan_wait_timeouts.argtypes = [vp]
+    L.nddwt_slab_route.argtypes = [c.c_int64, c.c_int, c.c_int, c.c_int, c.c_int64, c.c_int64, i64p, c.c_int]
     _lib = L
     return L
+
+
+def slab_route(n_last, world, rank, which, below, above):
+    """Host-only: runs (owner, first local plane, count, first halo slot) of rank's halo (nddwt_slab_route)."""
+    cap = 4 * (int(below) + int(above) + 1)
+    buf = (ctypes.c_int64 * (4 * cap))()
+    n = lib().nddwt_slab_route(int(n_last), int(world), int(rank), int(which), int(below), int(above), buf, cap)
+    if n < 0:
+        check(n)
+    return [tuple(int(buf[4 * k + i]) for i in range(4)) for k in range(n)]
 
 
 def check(rc):
@@ -206,3 +244,102 @@ class Plan:
 
     def rec_level_slab_stage2(self, level_index, u_lo, u_hi, halo_lo, halo_hi, a_out, stream=0):
         check(lib().nddwt_rec_level_slab_stage2(self.handle, level_index, u_lo, u_hi, halo_lo, halo_hi, a_out, stream))
+
+
+class MultiPlan:
+    """Owns one nddwt_mplan handle: the multi-GPU plan (slabs along the last dim, peer-memory halo pushes).
+
+    MultiPlan(dims, wnames, dtype, l2, devices=[...])            one process drives the listed devices
+    MultiPlan(dims, wnames, dtype, l2, rank=r, world=P, device=d) one rank of a one-process-per-GPU job; call
+        `connect(all_gather)` before the first transform (all_gather: bytes -> list of every rank's bytes)."""
+
+    def __init__(self, dims, wnames, dtype_code, pres_l2_norm, devices=None, rank=None, world=None, device=0):
+        L = lib()
+        self.ndims = len(dims)
+        self.dims = tuple(int(d) for d in dims)
+        arr = (ctypes.c_int64 * self.ndims)(*self.dims)
+        names = (ctypes.c_char_p * self.ndims)(*[str(w).encode() for w in wnames])
+        h = ctypes.c_void_p()
+        if rank is None:
+            devices = list(devices if devices is not None else [0])
+            darr = (ctypes.c_int * len(devices))(*devices)
+            check(L.nddwt_mplan_create(ctypes.byref(h), self.ndims, arr, names, dtype_code, int(bool(pres_l2_norm)),
+                                       len(devices), darr))
+            self.devices = devices
+        else:
+            check(L.nddwt_mplan_create_rank(ctypes.byref(h), self.ndims, arr, names, dtype_code,
+                                            int(bool(pres_l2_norm)), int(rank), int(world), int(device)))
+            self.devices = [device]
+        self.handle = h
+        self.dtype_code = dtype_code
+        self.rank = rank
+        self.world = int(L.nddwt_mplan_world(h))
+        self.num_local = int(L.nddwt_mplan_num_local(h))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().nddwt_mplan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def connect(self, all_gather):
+        """Exchange the IPC export blobs (rank plans).  all_gather(bytes) -> [bytes of rank 0, ..., rank P-1]."""
+        n = int(lib().nddwt_mplan_export_size())
+        blob = (ctypes.c_char * n)()
+        check(lib().nddwt_mplan_export(self.handle, blob))
+        blobs = all_gather(bytes(blob))
+        joined = b"".join(blobs)
+        assert len(joined) == n * self.world
+        buf = (ctypes.c_char * len(joined)).from_buffer_copy(joined)
+        check(lib().nddwt_mplan_import(self.handle, buf))
+
+    def slab(self, rank):
+        s, c = ctypes.c_int64(0), ctypes.c_int64(0)
+        check(lib().nddwt_mplan_slab(self.handle, rank, ctypes.byref(s), ctypes.byref(c)))
+        return s.value, c.value
+
+    @property
+    def separable(self):
+        return bool(lib().nddwt_mplan_is_separable(self.handle))
+
+    def set_dilations(self, dil):
+        a = (ctypes.c_int * len(dil))(*[int(v) for v in dil])
+        check(lib().nddwt_mplan_set_dilations(self.handle, a, len(dil)))
+
+    def set_kernel_mode(self, mode):
+        check(lib().nddwt_mplan_set_kernel_mode(self.handle, int(mode)))
+
+    def set_param(self, name, value):
+        check(lib().nddwt_mplan_set_param(self.handle, str(name).encode(), int(value)))
+
+    @staticmethod
+    def _ptrs(vals):
+        return (ctypes.c_void_p * len(vals))(*[int(v) if v else None for v in vals])
+
+    def dec(self, x_ptrs, c_ptrs, level, streams=None):
+        st = self._ptrs(streams) if streams is not None else None
+        check(lib().nddwt_mplan_dec(self.handle, self._ptrs(x_ptrs), self._ptrs(c_ptrs), int(level), st))
+
+    def rec(self, c_ptrs, x_ptrs, level, streams=None):
+        st = self._ptrs(streams) if streams is not None else None
+        check(lib().nddwt_mplan_rec(self.handle, self._ptrs(c_ptrs), self._ptrs(x_ptrs), int(level), st))
+
+    def sync(self):
+        check(lib().nddwt_mplan_sync(self.handle))
+
+    @property
+    def launches(self):
+        return int(lib().nddwt_mplan_launch_count(self.handle))
+
+    @property
+    def halo_bytes(self):
+        return int(lib().nddwt_mplan_halo_bytes(self.handle))
+
+    @property
+    def wait_timeouts(self):
+        return int(lib().nddwt_mplan_wait_timeouts(self.handle))

@@ -376,3 +376,106 @@ class SlabTransform:
                 self.engine.rec_stage2(j, self.u[0], self.u[1], None, None, dst)
             a = dst
         return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Peer-memory transport: the exchange lives inside the library (nddwt_mplan_*, csrc/nddwt_multi.cu):
+# halo planes are pushed straight into the neighbours' inboxes with copy-engine peer copies, ranks
+# order themselves with flags in peer memory (one process per GPU) or CUDA events (one process for
+# all GPUs).  torch.distributed is only used once, to all-gather the IPC handles.
+class PeerSlabTransform:
+    """One rank of a one-process-per-GPU job; same tensor layout as SlabTransform
+    ([n_local, N_{d-1}, ..., N_1] slabs, coefficient slab [nb, n_local, ...])."""
+
+    transport = "peer-memory pushes (CUDA IPC + copy engines), flags in peer memory"
+
+    def __init__(self, sizes, wnames, dtype_code, pres_l2_norm, rank, world, device_index, group=None, dilations=None):
+        from ._lib import MultiPlan
+        self.sizes = tuple(int(s) for s in sizes)
+        self.d = len(self.sizes)
+        self.rank, self.world, self.device_index = rank, world, device_index
+        self.plan = MultiPlan(self.sizes, wnames, dtype_code, pres_l2_norm, rank=rank, world=world, device=device_index)
+        if dilations is not None:
+            self.plan.set_dilations(dilations)
+        self.start, self.n_local = self.plan.slab(rank)
+        self.parts = [self.plan.slab(r) for r in range(world)]
+        self.local_shape = (self.n_local,) + tuple(reversed(self.sizes[:-1]))
+        self.overlap = self.plan.separable
+        self.scatter = self.plan.separable
+        if world > 1:
+            def all_gather(blob):
+                out = [None] * world
+                dist.all_gather_object(out, blob, group=group)
+                return out
+            self.plan.connect(all_gather)
+
+    def num_bands(self, level):
+        nd = 1 << self.d
+        return nd + (nd - 1) * (level - 1)
+
+    def _stream(self):
+        return [torch.cuda.current_stream(self.device_index).cuda_stream]
+
+    def dec(self, x_local, level, out=None):
+        if out is None:
+            out = torch.empty((self.num_bands(level),) + self.local_shape, dtype=x_local.dtype, device=x_local.device)
+        assert x_local.is_contiguous() and out.is_contiguous() and tuple(x_local.shape) == self.local_shape
+        self.plan.dec([x_local.data_ptr()], [out.data_ptr()], level, self._stream())
+        return out
+
+    def rec(self, coeffs, out=None):
+        nd = 1 << self.d
+        level = 1 + (coeffs.shape[0] - nd) // (nd - 1)
+        if out is None:
+            out = torch.empty(self.local_shape, dtype=coeffs.dtype, device=coeffs.device)
+        assert coeffs.is_contiguous() and out.is_contiguous()
+        self.plan.rec([coeffs.data_ptr()], [out.data_ptr()], level, self._stream())
+        return out
+
+
+class MultiGpuTransform:
+    """One process drives several GPUs (or several emulated ranks on one GPU: repeat a device index).
+    x / coefficient slabs are lists with one tensor per rank on that rank's device."""
+
+    def __init__(self, sizes, wnames, dtype_code, pres_l2_norm, devices, dilations=None, kernel_mode=0):
+        from ._lib import MultiPlan
+        self.sizes = tuple(int(s) for s in sizes)
+        self.d = len(self.sizes)
+        self.devices = list(devices)
+        self.world = len(self.devices)
+        self.plan = MultiPlan(self.sizes, wnames, dtype_code, pres_l2_norm, devices=self.devices)
+        if kernel_mode:
+            self.plan.set_kernel_mode(kernel_mode)
+        if dilations is not None:
+            self.plan.set_dilations(dilations)
+        self.parts = [self.plan.slab(r) for r in range(self.world)]
+        self.local_shapes = [(c,) + tuple(reversed(self.sizes[:-1])) for (_, c) in self.parts]
+
+    def num_bands(self, level):
+        nd = 1 << self.d
+        return nd + (nd - 1) * (level - 1)
+
+    def scatter_input(self, x_full_base):
+        """[N_d, ..., N_1] tensor (any device) -> list of per-rank slabs on the ranks' devices."""
+        return [x_full_base[s:s + c].to("cuda:%d" % dev).contiguous() for (s, c), dev in zip(self.parts, self.devices)]
+
+    def dec(self, xs, level, outs=None):
+        nb = self.num_bands(level)
+        if outs is None:
+            outs = [torch.empty((nb,) + shp, dtype=x.dtype, device=x.device) for x, shp in zip(xs, self.local_shapes)]
+        for dev in set(self.devices):
+            torch.cuda.synchronize(dev)          # plan-owned streams: inputs must be complete
+        self.plan.dec([x.data_ptr() for x in xs], [o.data_ptr() for o in outs], level)
+        self.plan.sync()
+        return outs
+
+    def rec(self, coeffs, outs=None):
+        nd = 1 << self.d
+        level = 1 + (coeffs[0].shape[0] - nd) // (nd - 1)
+        if outs is None:
+            outs = [torch.empty(shp, dtype=c.dtype, device=c.device) for c, shp in zip(coeffs, self.local_shapes)]
+        for dev in set(self.devices):
+            torch.cuda.synchronize(dev)
+        self.plan.rec([c.data_ptr() for c in coeffs], [o.data_ptr() for o in outs], level)
+        self.plan.sync()
+        return outs

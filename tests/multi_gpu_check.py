@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
-"""Multi-GPU parity check (run under torchrun on a box with >= 2 GPUs; not collected by pytest):
-every rank transforms its slab of a seeded global array with the CUDA slab kernels + NCCL halo
-exchange (overlapped schedule) and compares with the oracle's full-array transform.
+"""Multi-GPU parity check, one process per GPU (run under torchrun on a box with >= 2 GPUs; spawned by
+tests/test_gpu_multi.py::test_one_process_per_gpu_torchrun): every rank transforms its slab of a seeded
+global array and compares with the oracle's full-array transform, once per transport: the library's
+peer-memory pushes (nddwt_mplan_*, CUDA IPC + flags) and the NCCL send/recv schedule (SlabTransform).
 
   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_check.py
 """
@@ -39,18 +40,29 @@ def main():
         parts = slab.slab_partition(sizes[-1], world)
         s, c = parts[rank]
         xl = torch.from_numpy(np.ascontiguousarray(x[..., s:s + c].transpose(*reversed(range(d))))).to(dev)
-        eng = slab.CudaSlabEngine(tuple(sizes[:-1]) + (c,), sizes[-1], wn, _lib.NDDWT_C64, l2, lr)
-        tr = slab.SlabTransform(sizes, wn, level, eng, L, rank, world, device=dev, dtype=torch.complex64)
-        y = tr.dec(xl, level)
-        xr = tr.rec(y)
-        torch.cuda.synchronize()
         yo = orc.dec_direct(x.astype(np.complex128), wn, level, bool(l2))
-        y_np = y.cpu().numpy().transpose(*reversed(range(d + 1)))
-        e_dec = orc.rel_l2(y_np, yo[..., s:s + c, :])
-        e_rec = orc.rel_l2(xr.cpu().numpy().transpose(*reversed(range(d))), x[..., s:s + c])
-        worst = max(worst, e_dec, e_rec)
-        print("rank %d %s %s J%d overlap=%s: dec %.2e rec %.2e" % (rank, sizes, wname, level, tr.overlap, e_dec, e_rec),
-              flush=True)
+        for transport in ("peer", "nccl"):
+            if transport == "peer":
+                tr = slab.PeerSlabTransform(sizes, wn, _lib.NDDWT_C64, l2, rank, world, lr)
+                assert (tr.start, tr.n_local) == (s, c)
+            else:
+                eng = slab.CudaSlabEngine(tuple(sizes[:-1]) + (c,), sizes[-1], wn, _lib.NDDWT_C64, l2, lr)
+                tr = slab.SlabTransform(sizes, wn, level, eng, L, rank, world, device=dev, dtype=torch.complex64)
+            for rep in range(2):            # second pass: buffers, flags and sequence numbers are reused
+                y = tr.dec(xl, level)
+                xr = tr.rec(y)
+            torch.cuda.synchronize()
+            if transport == "peer":
+                tr.plan.sync()
+                assert tr.plan.wait_timeouts == 0
+            y_np = y.cpu().numpy().transpose(*reversed(range(d + 1)))
+            e_dec = orc.rel_l2(y_np, yo[..., s:s + c, :])
+            e_rec = orc.rel_l2(xr.cpu().numpy().transpose(*reversed(range(d))), x[..., s:s + c])
+            worst = max(worst, e_dec, e_rec)
+            print("rank %d %s %s J%d %s overlap=%s: dec %.2e rec %.2e" % (rank, sizes, wname, level, transport,
+                                                                          tr.overlap, e_dec, e_rec), flush=True)
+            dist.barrier()
+            del tr
     t = torch.tensor([worst], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.destroy_process_group()

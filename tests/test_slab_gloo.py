@@ -29,6 +29,22 @@ def test_partition_and_halo_sources():
     assert lo == [(0, 0), (0, 1), (0, 2)] and hi == [(2, 0), (2, 1), (0, 0), (0, 1)]
 
 
+def test_library_routing_matches_python_routing():
+    """The C library's halo routing (nddwt_slab_route, used by the peer-memory schedule of nddwt_mplan_*)
+    resolves every halo plane to the same (owner, local index) as slab.halo_sources."""
+    _lib = importlib.import_module("non-decimated_wavelets_b200._lib")
+    for n, world in [(32, 8), (7, 3), (48, 8), (9, 2), (5, 5), (16, 1)]:
+        for below, above in [(3, 4), (4, 3), (0, 1), (9, 10), (12, 16)]:
+            for rank in range(world):
+                lo, hi = slab.halo_sources(n, world, rank, below, above)
+                for which, ref in ((0, lo), (1, hi)):
+                    got = []
+                    for owner, idx, cnt, off in _lib.slab_route(n, world, rank, which, below, above):
+                        assert off == len(got)
+                        got += [(owner, idx + i) for i in range(cnt)]
+                    assert got == ref, (n, world, rank, which, below, above)
+
+
 class NumpyEngine:
     """Slab compute stand-in: periodic filtering along dims 1..d-1, halo-fed along the last dim."""
 
