@@ -189,6 +189,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kernel-mode", type=int, default=0)
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="N>1: halo transport (peer-memory pushes inside the library, or NCCL send/recv)")
+    ap.add_argument("--no-same-workload", action="store_true", help="N>1: skip the sharded cfg5 run")
     args = ap.parse_args()
 
     # N=1: cfg4 (the config the target is quoted on) needs 197.6 GB of coefficients and does not fit one

@@ -209,8 +209,8 @@ NDDWT_API int nddwt_mplan_set_kernel_mode(nddwt_mplan *mplan, int mode);
 NDDWT_API int nddwt_mplan_set_param(nddwt_mplan *mplan, const char *name, int64_t value);
 
 /* y = dec(x, level) / x = rec(y) on slabs.  x_slabs / coeff_slabs: one DEVICE pointer per local rank (in
- * rank order) on that rank's device; streams: one cudaStream_t per local rank, or NULL for plan-owned
- * streams.  Asynchronous; nddwt_mplan_sync waits for every local rank.  In the one-process-per-GPU form
+ * rank order) on that rank's device; streams: one cudaStream_t per local rank (a NULL entry is the legacy
+ * default stream), or a NULL array for plan-owned streams.  Asynchronous; nddwt_mplan_sync waits for every local rank.  In the one-process-per-GPU form
  * every rank must make the same calls in the same order. */
 NDDWT_API int nddwt_mplan_dec(nddwt_mplan *mplan, const void *const *x_slabs, void *const *coeff_slabs, int level,
                               void *const *streams);

@@ -639,7 +639,7 @@ int nddwt_mplan_dec(nddwt_mplan *mp, const void *const *x_slabs, void *const *co
     if (rc) return rc;
     const int nl = (int)mp->local.size(), nd = 1 << mp->ndims, L = mp->L_last;
     std::vector<cudaStream_t> cs(nl);
-    for (int i = 0; i < nl; ++i) cs[i] = (streams && streams[i]) ? reinterpret_cast<cudaStream_t>(streams[i]) : mp->local[i].cs;
+    for (int i = 0; i < nl; ++i) cs[i] = streams ? reinterpret_cast<cudaStream_t>(streams[i]) : mp->local[i].cs;   // a NULL entry is the legacy default stream
     if (mp->world == 1) return nddwt_dec(mp->local[0].plan, x_slabs[0], coeff_slabs[0], level, cs[0]);
     std::vector<const void *> a_in(x_slabs, x_slabs + nl);
     for (int j = 1; j <= level; ++j) {
@@ -689,7 +689,7 @@ int nddwt_mplan_rec(nddwt_mplan *mp, const void *const *coeff_slabs, void *const
     if (rc) return rc;
     const int nl = (int)mp->local.size(), nd = 1 << mp->ndims, L = mp->L_last;
     std::vector<cudaStream_t> cs(nl);
-    for (int i = 0; i < nl; ++i) cs[i] = (streams && streams[i]) ? reinterpret_cast<cudaStream_t>(streams[i]) : mp->local[i].cs;
+    for (int i = 0; i < nl; ++i) cs[i] = streams ? reinterpret_cast<cudaStream_t>(streams[i]) : mp->local[i].cs;   // a NULL entry is the legacy default stream
     if (mp->world == 1) return nddwt_rec(mp->local[0].plan, coeff_slabs[0], x_slabs[0], level, cs[0]);
     std::vector<const void *> a(coeff_slabs, coeff_slabs + nl);     // slot 0 = deepest approximation
     std::vector<std::vector<void *>> bands(nl, std::vector<void *>(nd));

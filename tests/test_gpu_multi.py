@@ -120,7 +120,7 @@ def test_real_devices_one_process():
     if n < 2:
         pytest.skip("needs >= 2 GPUs (the emulated-rank tests cover the schedule on one)")
     for sizes, wname, level, l2 in [((32, 24, 16, 4 * n), "db4", 3, 0), ((40, 20, 12, 2 * n + 1), "db2", 2, 1),
-                                    ((64, 32, 3 * n), "db4", 2, 0)]:
+                                    ((64, 32, max(3 * n, 9)), "db4", 2, 0)]:
         x, y, xr, c, xc, tr = _run(sizes, wname, level, l2, list(range(n)))
         assert orc.rel_l2(y, orc.dec_direct(x.astype(np.complex128), wname, level, bool(l2))) <= 1e-5
         assert orc.rel_l2(xr, x) <= 1e-5
