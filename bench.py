@@ -192,6 +192,8 @@ def main():
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="N>1: halo transport (peer-memory pushes inside the library, or NCCL send/recv)")
     ap.add_argument("--no-same-workload", action="store_true", help="N>1: skip the sharded cfg5 run")
+    ap.add_argument("--z-chunks", type=int, default=0, help="N>1, peer transport: dim-3 chunks of the pipelined exchange (0 = library default)")
+    ap.add_argument("--comm-streams", type=int, default=0, help="N>1, peer transport: copy streams per rank (0 = library default)")
     args = ap.parse_args()
 
     # N=1: cfg4 (the config the target is quoted on) needs 197.6 GB of coefficients and does not fit one

@@ -20,6 +20,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+COMM_STREAMS = 0
+Z_CHUNKS = 0
+
+
 def _make_transform(slab, _lib, nd, transport, sizes, wname, level, dtype, rank, world, local_rank, dev):
     import torch
     d = len(sizes)
@@ -28,6 +32,10 @@ def _make_transform(slab, _lib, nd, transport, sizes, wname, level, dtype, rank,
     tdt = torch.complex64 if dtype == "complex64" else torch.complex128
     if transport == "peer":
         tr = slab.PeerSlabTransform(sizes, wn, code, 0, rank, world, local_rank)
+        if COMM_STREAMS:
+            tr.plan.set_param("comm_streams", COMM_STREAMS)
+        if Z_CHUNKS:
+            tr.plan.set_param("z_chunks", Z_CHUNKS)
         return tr, tr.plan
     L = len(nd.wave_filters(wname)[0])
     c0 = slab.slab_partition(sizes[-1], world)[rank][1]
@@ -157,6 +165,9 @@ def run_multi(args, wl_name, wl):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, pg_options=opts)
 
     transport = getattr(args, "transport", "peer")
+    global COMM_STREAMS, Z_CHUNKS
+    COMM_STREAMS = int(getattr(args, "comm_streams", 0) or 0)
+    Z_CHUNKS = int(getattr(args, "z_chunks", 0) or 0)
     fallback = None
     if transport == "peer":
         # every rank must agree on the transport: any failure anywhere switches all ranks to nccl
@@ -208,6 +219,31 @@ def run_multi(args, wl_name, wl):
     ms_per_step = _time_pairs(tr, x, y, xr, level, args.steps, 0, dev)
     clocks = sampler.stop() if sampler else None
     launches = plan.launches - l0
+    # per-kind device times of this rank (events around every launch, second pass; not part of the timed value)
+    kinds = ["analysis tile kernel", "synthesis tile kernel", "analysis last-dim pass", "synthesis last-dim pass + adds",
+             "generic pass", "halo pushes (comm stream)"]
+    ktimes = None
+    try:
+        for k in range(6):
+            plan.kernel_time(k)
+        plan.profile(True)
+        psteps = max(2, min(args.steps, 5))
+        for _ in range(psteps):
+            tr.dec(x, level, out=y)
+            tr.rec(y, out=xr)
+        torch.cuda.synchronize()
+        plan.profile(False)
+        ktimes = {}
+        for k in range(6):
+            tot, cnt = plan.kernel_time(k)
+            if cnt:
+                ktimes[kinds[k]] = {"ms_per_step": tot / psteps, "launches_per_step": cnt / psteps}
+        compute = sum(v["ms_per_step"] for n, v in ktimes.items() if not n.startswith("halo"))
+        ktimes["compute_kernels_ms_per_step"] = compute
+        ktimes["exposed_comm_ms_per_step"] = ms_per_step - compute
+        dist.barrier()
+    except Exception as exc:   # noqa: BLE001
+        ktimes = {"error": str(exc)[:160]}
     nvox = int(np.prod(sizes))
     esize = np.dtype(dtype).itemsize
     value = nvox / (ms_per_step * 1e-3) / 1e6
@@ -266,12 +302,12 @@ def run_multi(args, wl_name, wl):
                        "transport": ("peer memory: copy-engine pushes over NVLink into CUDA-IPC inboxes, flags in peer "
                                      "memory (nddwt_mplan_*)") if transport == "peer" else
                                     "NCCL send/recv per level (torch.distributed batch_isend_irecv)",
-                       "transport_fallback": fallback, "flag_wait_timeouts": timeouts,
+                       "transport_fallback": fallback, "flag_wait_timeouts": timeouts, "comm_streams": COMM_STREAMS or "default (1)", "z_chunks": Z_CHUNKS or "default (4)",
                        "l2": "per-GPU working set %.1f GB >> L2, no flush" % ((1 + nb) * nvox * esize / world / 1e9),
                        "pr_rel_err": pr_err, "dec_rel_err": e_dec, "parity_rec_rel_err": e_rec,
                        "parity_case": {"sizes": small, "what": "rank 0's slab of dec vs the oracle, reconstruction on every rank"},
                        "halo_bytes_per_rank_per_step": int(halo_bytes),
-                       "dec_ms_rank0": dec_ms, "rec_ms_rank0": rec_ms, "overlap": overlap, "scatter_exchange": scatter,
+                       "dec_ms_rank0": dec_ms, "rec_ms_rank0": rec_ms, "rank0_kernel_times": ktimes, "overlap": overlap, "scatter_exchange": scatter,
                        "scaling_comparable": "N=1 runs cfg5 (cfg4 needs 197.6 GB of coefficients); "
                                              "`same_workload` is cfg5 sharded over the same ranks",
                        "same_workload": same},

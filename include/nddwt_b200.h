@@ -99,7 +99,8 @@ NDDWT_API int64_t nddwt_plan_launch_count(const nddwt_plan *plan);
 /* Per-kernel timing with CUDA events on the launch stream (bench.py's roofline): switch on, run any
  * number of dec/rec calls, then read the accumulated device time and launch count of one kernel
  * kind (0 analysis 3-D tile kernel, 1 synthesis 3-D tile kernel, 2 analysis last-dim pass,
- * 3 synthesis last-dim pass, 4 generic separable pass).  Reading synchronises and clears that kind. */
+ * 3 synthesis last-dim pass incl. the adds of the multi-GPU exchange, 4 generic separable pass, 5 halo pushes of
+ * a multi-GPU plan).  Reading synchronises and clears that kind. */
 NDDWT_API int nddwt_plan_profile(nddwt_plan *plan, int on);
 NDDWT_API int nddwt_plan_kernel_time(nddwt_plan *plan, int kind, double *total_ms, int64_t *count);
 /* 1 if the last dec/rec of this plan ran the fused kernels, 0 if the generic ones. */
@@ -206,6 +207,8 @@ NDDWT_API int nddwt_mplan_slab(const nddwt_mplan *mplan, int rank, int64_t *star
 NDDWT_API int nddwt_mplan_is_separable(const nddwt_mplan *mplan); /* 1: overlapped scatter schedule (fused 4-D path) */
 NDDWT_API int nddwt_mplan_set_dilations(nddwt_mplan *mplan, const int *dil, int nlevels);  /* a-trous: halos (L-1)*dil */
 NDDWT_API int nddwt_mplan_set_kernel_mode(nddwt_mplan *mplan, int mode);
+/* "comm_streams" (1..4, default 2): every pushed run of planes is cut in that many pieces which travel on
+ * different streams / copy engines at once; other names are forwarded to the per-rank plans. */
 NDDWT_API int nddwt_mplan_set_param(nddwt_mplan *mplan, const char *name, int64_t value);
 
 /* y = dec(x, level) / x = rec(y) on slabs.  x_slabs / coeff_slabs: one DEVICE pointer per local rank (in
@@ -219,6 +222,10 @@ NDDWT_API int nddwt_mplan_rec(nddwt_mplan *mplan, const void *const *coeff_slabs
 NDDWT_API int nddwt_mplan_sync(nddwt_mplan *mplan);
 NDDWT_API int64_t nddwt_mplan_launch_count(const nddwt_mplan *mplan);
 NDDWT_API int64_t nddwt_mplan_halo_bytes(const nddwt_mplan *mplan);     /* bytes pushed to peers so far (local ranks) */
+/* nddwt_plan_profile / nddwt_plan_kernel_time of one local rank's plan; kind 5 = the pushes of a level
+ * (flag wait + peer copies + flag signal) timed on the rank's comm stream. */
+NDDWT_API int nddwt_mplan_profile(nddwt_mplan *mplan, int on);
+NDDWT_API int nddwt_mplan_kernel_time(nddwt_mplan *mplan, int local_index, int kind, double *total_ms, int64_t *count);
 NDDWT_API int nddwt_mplan_wait_timeouts(const nddwt_mplan *mplan);      /* peer flag waits that gave up (0 when healthy) */
 
 /* Host-only routing query (no device): the planes rank `rank` of `world` needs below (which = 0) or above

@@ -25,7 +25,7 @@ SYMBOLS = [
     "nddwt_mplan_import", "nddwt_mplan_destroy", "nddwt_mplan_world", "nddwt_mplan_num_local", "nddwt_mplan_slab",
     "nddwt_mplan_is_separable", "nddwt_mplan_set_dilations", "nddwt_mplan_set_kernel_mode", "nddwt_mplan_set_param",
     "nddwt_mplan_dec", "nddwt_mplan_rec", "nddwt_mplan_sync", "nddwt_mplan_launch_count", "nddwt_mplan_halo_bytes",
-    "nddwt_mplan_wait_timeouts", "nddwt_slab_route",
+    "nddwt_mplan_wait_timeouts", "nddwt_slab_route", "nddwt_mplan_profile", "nddwt_mplan_kernel_time",
     "nddwt_halo_planes", "nddwt_dec_level_slab", "nddwt_plan_is_separable", "nddwt_dec_level_slab_part", "nddwt_rec_level_slab_stage1_part", "nddwt_rec_level_slab_stage2_scatter", "nddwt_accumulate", "nddwt_rec_level_slab_stage1", "nddwt_rec_level_slab_stage2",
 ]
 
@@ -104,6 +104,8 @@ def lib():
     L.nddwt_mplan_halo_bytes.argtypes = [vp]
     L.nddwt_mplan_halo_bytes.restype = c.c_int64
     L.nddwt_mplan_wait_timeouts.argtypes = [vp]
+    L.nddwt_mplan_profile.argtypes = [vp, c.c_int]
+    L.nddwt_mplan_kernel_time.argtypes = [vp, c.c_int, c.c_int, dp, c.POINTER(c.c_int64)]
     L.nddwt_slab_route.argtypes = [c.c_int64, c.c_int, c.c_int, c.c_int, c.c_int64, c.c_int64, i64p, c.c_int]
     _lib = L
     return L
@@ -335,6 +337,14 @@ class MultiPlan:
     @property
     def launches(self):
         return int(lib().nddwt_mplan_launch_count(self.handle))
+
+    def profile(self, on):
+        check(lib().nddwt_mplan_profile(self.handle, int(bool(on))))
+
+    def kernel_time(self, kind, local_index=0):
+        ms, n = ctypes.c_double(0.0), ctypes.c_int64(0)
+        check(lib().nddwt_mplan_kernel_time(self.handle, local_index, kind, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
 
     @property
     def halo_bytes(self):

@@ -68,6 +68,8 @@ struct Dec3Params {
     int nhyp;           // hyperplanes per input array (1 for 3-D)
     int tiles1, tiles2, zc, nchunks;
     int halo_below;     // planes held by halo_lo
+    int zbase = 0, zcount = 0;   // dim-3 sub-range produced by this launch (zcount 0: all n3 planes); the
+                                 // ring still reads its L-1 neighbour planes around the range, periodic in n3
 };
 
 __device__ __forceinline__ int wrapi(int m, int n)
@@ -195,8 +197,8 @@ k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
     const int chunk = bid % p.nchunks;
     const int batch = bid / p.nchunks;
     const int a1 = t1 * T1, a2 = t2 * T2;
-    const int z0 = chunk * p.zc;
-    const int z1 = min(z0 + p.zc, p.n3);
+    const int z0 = p.zbase + chunk * p.zc;
+    const int z1 = min(z0 + p.zc, p.zbase + p.zcount);
     const int n1 = p.n1, n2 = p.n2, n3 = p.n3;
     const int64_t s3 = p.s3;
     const bool slab = (p.halo_lo != nullptr) || (p.halo_hi != nullptr);
@@ -388,6 +390,7 @@ struct Rec3Params {
     int prefetch;       // 0 none, 1 prefetch.global.L1 of the next plane's footprint, 2 prefetch.global.L2
     int cl1, cl2;       // thread-block cluster shape in tiles (cl1 x cl2 CTAs, 1 x 1 = no cluster)
     int hint;           // 1: stage the subband tiles with an L2 evict_last policy
+    int zbase = 0, zcount = 0;   // dim-3 sub-range of OUTPUT planes produced by this launch (zcount 0: all n3)
 };
 
 template <typename T, int L, int T2>
@@ -478,8 +481,8 @@ k_rec3_fused(const Rec3Params<T> p, const FusedTaps<T, L> tp)
     const int chunk = bid % p.nchunks;
     const int batch = bid / p.nchunks;
     const int a1 = t1 * T1, a2 = t2 * T2;
-    const int z0 = chunk * p.zc;
-    const int z1 = min(z0 + p.zc, p.n3);
+    const int z0 = p.zbase + chunk * p.zc;
+    const int z1 = min(z0 + p.zc, p.zbase + p.zcount);
     const int n1 = p.n1, n2 = p.n2, n3 = p.n3;
     const int64_t s3 = p.s3;
     const int bsel = batch / p.nhyp, bhyp = batch - bsel * p.nhyp;
@@ -774,8 +777,8 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp, const __grid_consta
     const int chunk = bid % p.nchunks;
     const int batch = bid / p.nchunks;
     const int a1 = t1 * T1, a2 = t2 * T2;
-    const int z0 = chunk * p.zc;
-    const int z1 = min(z0 + p.zc, p.n3);
+    const int z0 = p.zbase + chunk * p.zc;
+    const int z1 = min(z0 + p.zc, p.zbase + p.zcount);
     const int n1 = p.n1, n2 = p.n2, n3 = p.n3;
     const int64_t s3 = p.s3;
     const int bsel = batch / p.nhyp, bhyp = batch - bsel * p.nhyp;
@@ -865,7 +868,7 @@ k_rec3_bulk(const Rec3Params<T> p, const FusedTaps<T, L> tp, const __grid_consta
     // single chunk = the whole periodic dimension: every coefficient plane is staged exactly once; the
     // L-1 output planes that wrap around get the partial sum of the first steps stored early and the
     // rest added by L-1 flush steps at the end (periodic closure) instead of re-reading L-1 planes
-    const bool closed = (p.nchunks == 1);
+    const bool closed = (p.nchunks == 1 && p.zcount == p.n3);
     const int nsteps = closed ? (z1 - z0) : (z1 - z0) + L - 1;
     if (tid < 32) { if (tid == 0) mbar_expect_tx(bar, PLANE_BYTES); }
     __syncthreads();
@@ -1078,14 +1081,14 @@ k_rec3_rows(const Rec3Params<T> p, const FusedTaps<T, L> tp, const RowsGeo g)
     const int chunk = bid % p.nchunks;
     const int batch = bid / p.nchunks;
     const int a2 = t2 * T2;
-    const int z0 = chunk * p.zc;
-    const int z1 = min(z0 + p.zc, p.n3);
+    const int z0 = p.zbase + chunk * p.zc;
+    const int z1 = min(z0 + p.zc, p.zbase + p.zcount);
     const int n2 = p.n2, n3 = p.n3;
     const int64_t s3 = p.s3;
     const int bsel = batch / p.nhyp, bhyp = batch - bsel * p.nhyp;
     const int64_t boff = (int64_t)bhyp * p.s4;
 
-    const bool closed = (p.nchunks == 1);
+    const bool closed = (p.nchunks == 1 && p.zcount == p.n3);
     const int nsteps = closed ? (z1 - z0) : (z1 - z0) + L - 1;
     const int total = 4 * nsteps;                                 // pair steps
     const uint32_t stage_bytes = (uint32_t)(stage_elems * sizeof(T));
@@ -1459,8 +1462,9 @@ static int launch_dec3_v(nddwt_plan *p, const Dec3Params<T> &base, cudaStream_t 
     prm.tiles1 = (prm.n1 + G::T1 - 1) / G::T1;
     prm.tiles2 = (prm.n2 + T2 - 1) / T2;
     const int batches = prm.nhyp * (prm.in[1] ? 2 : 1);
-    prm.zc = pick_zc(prm.n3, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB);
-    prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
+    if (prm.zcount <= 0) { prm.zbase = 0; prm.zcount = prm.n3; }
+    prm.zc = pick_zc(prm.zcount, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB);
+    prm.nchunks = (prm.zcount + prm.zc - 1) / prm.zc;
     prm.halo_below = (L / 2 - 1);
     auto kern = k_dec3_fused<T, L, T2, NT, R2, MINB, CWSEL, RBM, ZINC>;
     NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));   // per-device attribute: set on every launch
@@ -1567,8 +1571,9 @@ static int launch_rec3_v(nddwt_plan *p, const Rec3Params<T> &base, cudaStream_t 
     prm.tiles1 = (prm.n1 + G::T1 - 1) / G::T1;
     prm.tiles2 = (prm.n2 + T2 - 1) / T2;
     const int batches = prm.nhyp * (prm.out[1] ? 2 : 1);
-    prm.zc = pick_zc_rec(prm.n3, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB);
-    prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
+    if (prm.zcount <= 0) { prm.zbase = 0; prm.zcount = prm.n3; }
+    prm.zc = pick_zc_rec(prm.zcount, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB);
+    prm.nchunks = (prm.zcount + prm.zc - 1) / prm.zc;
     prm.prefetch = tuning_env("NDDWT_PREFETCH", 0);   // prefetch.global.L1/L2 of the next plane: no gain (profiles/)
     p->last_rec_kernel = 1;
     auto kern = k_rec3_fused<T, L, T2, NT, R2, MINB>;
@@ -1632,8 +1637,9 @@ static int launch_rec3_bulk(nddwt_plan *p, const Rec3Params<T> &base, cudaStream
     prm.tiles1 = (prm.n1 + G::T1 - 1) / G::T1;
     prm.tiles2 = (prm.n2 + T2 - 1) / T2;
     const int batches = prm.nhyp * (prm.out[1] ? 2 : 1);
-    prm.zc = pick_zc_rec(prm.n3, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB, true);
-    prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
+    if (prm.zcount <= 0) { prm.zbase = 0; prm.zcount = prm.n3; }
+    prm.zc = pick_zc_rec(prm.zcount, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB, prm.zcount == prm.n3);
+    prm.nchunks = (prm.zcount + prm.zc - 1) / prm.zc;
     prm.prefetch = 0;
     prm.cl1 = prm.cl2 = 1;
     prm.hint = tuning_env("NDDWT_L2HINT", 0);         // evict_last hints on the staged tiles: no effect (profiles/)
@@ -1706,8 +1712,9 @@ static int launch_rec3_rows_n(nddwt_plan *p, const Rec3Params<T> &base, cudaStre
     prm.tiles1 = 1;
     prm.tiles2 = (prm.n2 + T2 - 1) / T2;
     const int batches = prm.nhyp * (prm.out[1] ? 2 : 1);
-    prm.zc = pick_zc_rec(prm.n3, prm.tiles2 * batches, L - 1, 148, true);
-    prm.nchunks = (prm.n3 + prm.zc - 1) / prm.zc;
+    if (prm.zcount <= 0) { prm.zbase = 0; prm.zcount = prm.n3; }
+    prm.zc = pick_zc_rec(prm.zcount, prm.tiles2 * batches, L - 1, 148, prm.zcount == prm.n3);
+    prm.nchunks = (prm.zcount + prm.zc - 1) / prm.zc;
     {
         // one CTA per SM: needs enough CTAs (row blocks x z-chunks x batches) to fill most of the machine once
         // (one rank's half-level of cfg4 on 8 GPUs is 128 blocks; a 256^3 volume is 32 row blocks x 4 chunks of
@@ -1853,21 +1860,36 @@ static int ensure_fused_scratch(nddwt_plan *p, size_t bytes)
     return 0;
 }
 
+// element sub-range of the hyperplane for the passes that are pointwise in dims 1..d-1 (multi-GPU pipelining)
+static void plane_range(const nddwt_plan *p, const ZRange &zr, int64_t s4, int64_t *e0, int64_t *en)
+{
+    *e0 = 0;
+    *en = s4;
+    if (zr.zn > 0 && p->ndims == 4) {
+        const int64_t s3 = p->dims[0] * p->dims[1];
+        *e0 = (int64_t)zr.z0 * s3;
+        *en = (int64_t)zr.zn * s3;
+    }
+}
+
 template <typename T, int L>
-static int launch_dec_last(nddwt_plan *p, const T *in, const LevelIO &io, T *out_lo, T *out_hi, cudaStream_t s)
+static int launch_dec_last(nddwt_plan *p, const T *in, const LevelIO &io, T *out_lo, T *out_hi, cudaStream_t s,
+                           const ZRange &zr = ZRange())
 {
     constexpr int VEC = 16 / (int)sizeof(T);
     const int d = p->ndims - 1;
     int64_t s4 = 1;
     for (int i = 0; i < d; ++i) s4 *= p->dims[i];
-    const int64_t nchunks = s4 / VEC;
+    int64_t e0, en;
+    plane_range(p, zr, s4, &e0, &en);
+    const int64_t nchunks = en / VEC;
     const int n4 = (int)p->dims[d];
     const unsigned grid = (unsigned)((nchunks + 255) / 256);
+    const T *hl = reinterpret_cast<const T *>(io.halo_lo), *hh = reinterpret_cast<const T *>(io.halo_hi);
     {
         LaunchTimer lt(p, KIND_DEC_LAST, s);
-        k_dec_last<T, L><<<grid, 256, 0, s>>>(in, reinterpret_cast<const T *>(io.halo_lo),
-                                             reinterpret_cast<const T *>(io.halo_hi), out_lo, out_hi, nchunks, n4, s4,
-                                             L / 2 - 1, make_last_taps<T, L>(p, false));
+        k_dec_last<T, L><<<grid, 256, 0, s>>>(in + e0, hl ? hl + e0 : nullptr, hh ? hh + e0 : nullptr, out_lo + e0,
+                                             out_hi + e0, nchunks, n4, s4, L / 2 - 1, make_last_taps<T, L>(p, false));
     }
     p->launches++;
     NDDWT_CUDA(cudaGetLastError());
@@ -1897,19 +1919,21 @@ static int launch_rec_last(nddwt_plan *p, const T *u_lo, const T *u_hi, const Le
 
 template <typename T, int L>
 static int launch_rec_last_scatter(nddwt_plan *p, const T *u_lo, const T *u_hi, T *out, T *over_lo, T *over_hi,
-                                   cudaStream_t s)
+                                   cudaStream_t s, const ZRange &zr = ZRange())
 {
     constexpr int VEC = 16 / (int)sizeof(T);
     const int d = p->ndims - 1;
     int64_t s4 = 1;
     for (int i = 0; i < d; ++i) s4 *= p->dims[i];
-    const int64_t nchunks = s4 / VEC;
+    int64_t e0, en;
+    plane_range(p, zr, s4, &e0, &en);
+    const int64_t nchunks = en / VEC;
     const int n4 = (int)p->dims[d];
     const unsigned grid = (unsigned)((nchunks + 255) / 256);
     {
         LaunchTimer lt(p, KIND_REC_LAST, s);
-        k_rec_last_scatter<T, L><<<grid, 256, 0, s>>>(u_lo, u_hi, out, over_lo, over_hi, nchunks, n4, s4,
-                                                     make_last_taps<T, L>(p, true));
+        k_rec_last_scatter<T, L><<<grid, 256, 0, s>>>(u_lo + e0, u_hi + e0, out + e0, over_lo + e0, over_hi + e0, nchunks,
+                                                     n4, s4, make_last_taps<T, L>(p, true));
     }
     p->launches++;
     NDDWT_CUDA(cudaGetLastError());
@@ -1918,13 +1942,13 @@ static int launch_rec_last_scatter(nddwt_plan *p, const T *u_lo, const T *u_hi, 
 
 template <typename T>
 static int dispatch_rec_last_scatter(nddwt_plan *p, const void *u_lo, const void *u_hi, void *out, void *over_lo,
-                                     void *over_hi, cudaStream_t s);
+                                     void *over_hi, cudaStream_t s, const ZRange &zr);
 
 // part: 0 = whole level; 1 = dim-4 pass only (the one that needs the slab halos);
 //       2 = tile pass on the lo4 half (bands 0..7, incl. the approximation); 3 = tile pass on the hi4 half
 template <typename T, int L>
 static int dec4_level(nddwt_plan *p, const void *a_in, const LevelIO &io, void *const *out_bands, cudaStream_t s,
-                      int part = 0)
+                      int part = 0, const ZRange &zr = ZRange())
 {
     const size_t band_bytes = (size_t)p->numel * p->esize;
     int rc = ensure_fused_scratch(p, 2 * band_bytes);
@@ -1932,10 +1956,11 @@ static int dec4_level(nddwt_plan *p, const void *a_in, const LevelIO &io, void *
     T *lo4 = reinterpret_cast<T *>(p->fused_scratch);
     T *hi4 = lo4 + p->numel;
     if (part == 0 || part == 1) {
-        rc = launch_dec_last<T, L>(p, reinterpret_cast<const T *>(a_in), io, lo4, hi4, s);
+        rc = launch_dec_last<T, L>(p, reinterpret_cast<const T *>(a_in), io, lo4, hi4, s, zr);
         if (rc || part == 1) return rc;
     }
     Dec3Params<T> prm;
+    if (zr.zn > 0) { prm.zbase = zr.z0; prm.zcount = zr.zn; }
     prm.halo_lo = nullptr;
     prm.halo_hi = nullptr;
     prm.n1 = (int)p->dims[0];
@@ -1959,9 +1984,11 @@ static int dec4_level(nddwt_plan *p, const void *a_in, const LevelIO &io, void *
 
 // part: 0 = both halves; 1 = u_lo half (bands 0..7, needs the approximation band); 2 = u_hi half (bands 8..15)
 template <typename T, int L>
-static int rec4_stage1(nddwt_plan *p, const void *const *in_bands, T *u_lo, T *u_hi, cudaStream_t s, int part = 0)
+static int rec4_stage1(nddwt_plan *p, const void *const *in_bands, T *u_lo, T *u_hi, cudaStream_t s, int part = 0,
+                       const ZRange &zr = ZRange())
 {
     Rec3Params<T> prm;
+    if (zr.zn > 0) { prm.zbase = zr.z0; prm.zcount = zr.zn; }
     if (part == 0) {
         for (int b = 0; b < 16; ++b) prm.in[b] = reinterpret_cast<const T *>(in_bands[b]);
         prm.out[0] = u_lo;
@@ -2006,9 +2033,9 @@ static int rec4_level(nddwt_plan *p, const void *const *in_bands, void *a_out, c
 
 template <typename T>
 static int dispatch_dec4(nddwt_plan *p, const void *a_in, const LevelIO &io, void *const *out_bands, cudaStream_t s,
-                         int part = 0)
+                         int part = 0, const ZRange &zr = ZRange())
 {
-    NDDWT_L_SWITCH(p->L[0], (dec4_level<T, LL>(p, a_in, io, out_bands, s, part)));
+    NDDWT_L_SWITCH(p->L[0], (dec4_level<T, LL>(p, a_in, io, out_bands, s, part, zr)));
 }
 template <typename T>
 static int dispatch_rec4(nddwt_plan *p, const void *const *in_bands, void *a_out, cudaStream_t s)
@@ -2017,9 +2044,9 @@ static int dispatch_rec4(nddwt_plan *p, const void *const *in_bands, void *a_out
 }
 template <typename T>
 static int dispatch_rec4_stage1(nddwt_plan *p, const void *const *in_bands, void *u_lo, void *u_hi, cudaStream_t s,
-                                int part = 0)
+                                int part = 0, const ZRange &zr = ZRange())
 {
-    NDDWT_L_SWITCH(p->L[0], (rec4_stage1<T, LL>(p, in_bands, reinterpret_cast<T *>(u_lo), reinterpret_cast<T *>(u_hi), s, part)));
+    NDDWT_L_SWITCH(p->L[0], (rec4_stage1<T, LL>(p, in_bands, reinterpret_cast<T *>(u_lo), reinterpret_cast<T *>(u_hi), s, part, zr)));
 }
 template <typename T>
 static int dispatch_rec_last(nddwt_plan *p, const void *u_lo, const void *u_hi, const LevelIO &io, void *a_out,
@@ -2032,12 +2059,12 @@ static int dispatch_rec_last(nddwt_plan *p, const void *u_lo, const void *u_hi, 
 
 template <typename T>
 static int dispatch_rec_last_scatter(nddwt_plan *p, const void *u_lo, const void *u_hi, void *out, void *over_lo,
-                                     void *over_hi, cudaStream_t s)
+                                     void *over_hi, cudaStream_t s, const ZRange &zr)
 {
     NDDWT_L_SWITCH(p->L[p->ndims - 1],
                    (launch_rec_last_scatter<T, LL>(p, reinterpret_cast<const T *>(u_lo), reinterpret_cast<const T *>(u_hi),
                                                    reinterpret_cast<T *>(out), reinterpret_cast<T *>(over_lo),
-                                                   reinterpret_cast<T *>(over_hi), s)));
+                                                   reinterpret_cast<T *>(over_hi), s, zr)));
 }
 
 // int-range guards: the tile kernels index planes with ints and put every CTA in grid.x
@@ -2071,17 +2098,17 @@ static bool fused_geometry_ok(const nddwt_plan *p)
     }
 
 int fused_rec_stage1(nddwt_plan *p, int dil, const void *const *in_bands, void *u_lo, void *u_hi, cudaStream_t s,
-                     int part)
+                     int part, const ZRange &zr)
 {
     if (dil != 1 || !uniform_taps(p) || p->ndims != 4 || !fused_geometry_ok(p)) return 1;
-    NDDWT_T_SWITCH(p, (dispatch_rec4_stage1<TT>(p, in_bands, u_lo, u_hi, s, part)));
+    NDDWT_T_SWITCH(p, (dispatch_rec4_stage1<TT>(p, in_bands, u_lo, u_hi, s, part, zr)));
 }
 
 int fused_rec_stage2_scatter(nddwt_plan *p, int dil, const void *u_lo, const void *u_hi, void *out, void *over_lo,
-                             void *over_hi, cudaStream_t s)
+                             void *over_hi, cudaStream_t s, const ZRange &zr)
 {
     if (dil != 1 || p->ndims != 4 || !fused_geometry_ok(p)) return 1;
-    NDDWT_T_SWITCH(p, (dispatch_rec_last_scatter<TT>(p, u_lo, u_hi, out, over_lo, over_hi, s)));
+    NDDWT_T_SWITCH(p, (dispatch_rec_last_scatter<TT>(p, u_lo, u_hi, out, over_lo, over_hi, s, zr)));
 }
 
 int accumulate_elems(nddwt_plan *p, void *dst, const void *src, int64_t nelem, cudaStream_t s)
@@ -2100,6 +2127,56 @@ int accumulate_elems(nddwt_plan *p, void *dst, const void *src, int64_t nelem, c
     return 0;
 }
 
+// dst plane += sum of up to ACC_MAXS source planes, for several planes in one launch (the adds of the
+// scatter-form synthesis exchange: every plane is read and written once however many overhangs land on it)
+__device__ __forceinline__ void acc_add(float &a, float b) { a += b; }
+__device__ __forceinline__ void acc_add(double &a, double b) { a += b; }
+__device__ __forceinline__ void acc_add(float4 &a, float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ void acc_add(double2 &a, double2 b) { a.x += b.x; a.y += b.y; }
+
+template <typename V>
+__global__ void __launch_bounds__(256) k_accumulate_planes(const AccParams prm, int64_t nvec)
+{
+    const AccItem it = prm.item[blockIdx.y];
+    V *dst = reinterpret_cast<V *>(it.dst);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        V a = dst[i];
+        for (int k = 0; k < it.ns; ++k) {
+            acc_add(a, reinterpret_cast<const V *>(it.src[k])[i]);
+        }
+        dst[i] = a;
+    }
+}
+
+int accumulate_planes(nddwt_plan *p, const AccParams &prm, int64_t plane_elems, cudaStream_t s)
+{
+    if (prm.n < 1) return 0;
+    const bool dbl = (p->dtype == NDDWT_F64 || p->dtype == NDDWT_C128);
+    const int64_t bytes = plane_elems * (int64_t)p->esize;
+    bool vec = bytes % 16 == 0;
+    for (int i = 0; i < prm.n && vec; ++i) {
+        vec = (reinterpret_cast<uintptr_t>(prm.item[i].dst) & 15) == 0;
+        for (int k = 0; k < prm.item[i].ns && vec; ++k) vec = (reinterpret_cast<uintptr_t>(prm.item[i].src[k]) & 15) == 0;
+    }
+    const int64_t n = vec ? bytes / 16 : bytes / (dbl ? 8 : 4);
+    const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (148 * 16 + prm.n - 1) / prm.n));
+    const dim3 grid(gx, (unsigned)prm.n);
+    {
+        LaunchTimer lt(p, KIND_REC_LAST, s);
+        if (vec) {
+            if (dbl) k_accumulate_planes<double2><<<grid, 256, 0, s>>>(prm, n);   // 16 bytes = (x, y)
+            else k_accumulate_planes<float4><<<grid, 256, 0, s>>>(prm, n);
+        } else {
+            if (dbl) k_accumulate_planes<double><<<grid, 256, 0, s>>>(prm, n);
+            else k_accumulate_planes<float><<<grid, 256, 0, s>>>(prm, n);
+        }
+    }
+    p->launches++;
+    NDDWT_CUDA(cudaGetLastError());
+    return 0;
+}
+
 bool fused_is_separable(const nddwt_plan *p)
 {
     if (p->kernel_mode != 0 || p->batch != 1 || p->ndims != 4 || !uniform_taps(p) || !fused_geometry_ok(p)) return false;
@@ -2110,10 +2187,10 @@ bool fused_is_separable(const nddwt_plan *p)
 
 // 4-D analysis level in parts (multi-GPU overlap); returns 1 when the plan has no fused 4-D path
 int fused_dec_level_part(nddwt_plan *p, int dil, int part, const void *a_in, const LevelIO &io,
-                         void *const *out_bands, cudaStream_t s)
+                         void *const *out_bands, cudaStream_t s, const ZRange &zr)
 {
     if (dil != 1 || !uniform_taps(p) || p->ndims != 4 || !fused_geometry_ok(p)) return 1;
-    NDDWT_T_SWITCH(p, (dispatch_dec4<TT>(p, a_in, io, out_bands, s, part)));
+    NDDWT_T_SWITCH(p, (dispatch_dec4<TT>(p, a_in, io, out_bands, s, part, zr)));
 }
 
 int fused_rec_stage2(nddwt_plan *p, int dil, const void *u_lo, const void *u_hi, const LevelIO &io, void *a_out,

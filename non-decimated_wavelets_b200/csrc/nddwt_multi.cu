@@ -32,6 +32,9 @@ enum {
     NCH = 8
 };
 
+constexpr int EV_RING = 64;   // events mode: one event per signal sequence number (mod ring), so that a wait enqueued
+                              // after several later signals still waits for ITS signal only
+
 struct Run { int owner; int64_t idx, cnt, off; };   // planes idx.. of `owner` fill halo slots off..
 
 struct Piece { int src, which; int64_t over_off, idx, cnt, stage_off; };   // overhang planes -> owner's planes idx..
@@ -40,7 +43,10 @@ struct RankCtx {
     int rank = 0, device = 0;
     nddwt_plan *plan = nullptr;
     int64_t start = 0, count = 0;
-    cudaStream_t cs = nullptr, ms = nullptr;   // plan-owned compute stream (when the caller passes none), comm stream
+    cudaStream_t cs = nullptr;                 // plan-owned compute stream (used when the caller passes none)
+    cudaStream_t ms = nullptr;                 // comm stream (high priority): flag waits / signals and copies
+    cudaStream_t mx[3] = {nullptr, nullptr, nullptr};   // extra copy streams: every pushed run is cut in pieces, one per stream / copy engine
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     char *arena = nullptr;                     // peer-visible: flags, halo inboxes, stage
     void *approx[2] = {nullptr, nullptr};
     void *u_lo = nullptr, *u_hi[2] = {nullptr, nullptr};
@@ -48,6 +54,7 @@ struct RankCtx {
     cudaEvent_t ev_prod = nullptr, ev_pushed = nullptr;
     bool pushed_once = false;
     std::vector<uint32_t> sent, expect;        // [world * NCH] flag sequence numbers
+    std::vector<uint32_t> rounds;              // [world * NCH] exchanges started towards a peer (FREE is raised once per exchange)
 };
 
 }  // namespace nddwt
@@ -70,7 +77,7 @@ struct nddwt_mplan {
     std::vector<int> local_index;            // rank -> index in `local` or -1
     std::vector<char *> peer_arena;          // [world] arena base as seen from this process
     std::vector<bool> peer_opened;
-    std::vector<cudaEvent_t> ev;             // events mode: [(a * world + b) * NCH + ch], recorded on a's stream
+    std::vector<cudaEvent_t> ev;             // events mode: [((a * world + b) * NCH + ch) * EV_RING + seq % EV_RING], recorded on a's stream
     std::vector<char> ev_recorded;
     bool separable = false;
     size_t off_flags = 0, off_inbox[2][2] = {{0, 0}, {0, 0}}, off_stage = 0, arena_bytes = 0;
@@ -78,6 +85,9 @@ struct nddwt_mplan {
     uint32_t *status_host = nullptr;         // mapped host word: number of flag waits that timed out
     int64_t extra_launches = 0;
     int64_t copies = 0, copy_bytes = 0;
+    int comm_streams = 1;                    // copy streams per rank (1..4), nddwt_mplan_set_param("comm_streams")
+    int z_chunks = 4;                        // separable 4-D plans: a level is issued in this many dim-3 chunks so that
+                                             // the halo planes of one chunk travel while the next chunk computes
 };
 
 namespace nddwt {
@@ -160,7 +170,7 @@ static int fab_signal(nddwt_mplan *mp, RankCtx &from, int to, int ch, cudaStream
         mp->extra_launches++;
         NDDWT_CUDA(cudaGetLastError());
     } else {
-        const size_t e = ((size_t)from.rank * mp->world + to) * NCH + ch;
+        const size_t e = (((size_t)from.rank * mp->world + to) * NCH + ch) * EV_RING + v % EV_RING;
         if (!mp->ev[e]) NDDWT_CUDA(cudaEventCreateWithFlags(&mp->ev[e], cudaEventDisableTiming));
         NDDWT_CUDA(cudaEventRecord(mp->ev[e], s));
         mp->ev_recorded[e] = 1;
@@ -181,7 +191,7 @@ static int fab_wait(nddwt_mplan *mp, RankCtx &at, int from, int ch, cudaStream_t
         mp->extra_launches++;
         NDDWT_CUDA(cudaGetLastError());
     } else {
-        const size_t e = ((size_t)from * mp->world + at.rank) * NCH + ch;
+        const size_t e = (((size_t)from * mp->world + at.rank) * NCH + ch) * EV_RING + value % EV_RING;
         if (mp->ev_recorded[e]) NDDWT_CUDA(cudaStreamWaitEvent(s, mp->ev[e], 0));
     }
     return 0;
@@ -190,6 +200,38 @@ static int fab_wait(nddwt_mplan *mp, RankCtx &at, int from, int ch, cudaStream_t
 static inline char *inbox_ptr(const nddwt_mplan *mp, int rank, int par, int which)
 {
     return mp->peer_arena[rank] + mp->off_inbox[par][which];
+}
+
+// one logical peer copy, cut into comm_streams pieces that run on different streams (copy engines) at once.
+// The caller brackets a group of copies with fork_streams / join_streams on the rank's main comm stream.
+static int peer_copy(nddwt_mplan *mp, RankCtx &r, char *dst, const char *src, size_t bytes)
+{
+    const int ns = mp->comm_streams;
+    const size_t piece = ((bytes + ns - 1) / ns + 255) / 256 * 256;
+    for (int i = 0; i < ns; ++i) {
+        const size_t o = (size_t)i * piece;
+        if (o >= bytes) break;
+        const size_t n = bytes - o < piece ? bytes - o : piece;
+        NDDWT_CUDA(cudaMemcpyAsync(dst + o, src + o, n, cudaMemcpyDefault, i == 0 ? r.ms : r.mx[i - 1]));
+    }
+    mp->copies++;
+    mp->copy_bytes += (int64_t)bytes;
+    return 0;
+}
+static int fork_streams(nddwt_mplan *mp, RankCtx &r)   // extra streams continue after what is queued on ms
+{
+    if (mp->comm_streams <= 1) return 0;
+    NDDWT_CUDA(cudaEventRecord(r.ev_fork, r.ms));
+    for (int i = 1; i < mp->comm_streams; ++i) NDDWT_CUDA(cudaStreamWaitEvent(r.mx[i - 1], r.ev_fork, 0));
+    return 0;
+}
+static int join_streams(nddwt_mplan *mp, RankCtx &r)   // ms continues after the pieces on the extra streams
+{
+    for (int i = 1; i < mp->comm_streams; ++i) {
+        NDDWT_CUDA(cudaEventRecord(r.ev_join[i - 1], r.mx[i - 1]));
+        NDDWT_CUDA(cudaStreamWaitEvent(r.ms, r.ev_join[i - 1], 0));
+    }
+    return 0;
 }
 
 struct PushSrc { const char *base; int64_t slot_shift[2]; };   // local array + extra slot offset per side (gather-form u_hi)
@@ -201,6 +243,7 @@ static int push_halos(nddwt_mplan *mp, RankCtx &r, const PushSrc *srcs, int nsrc
 {
     NDDWT_CUDA(cudaSetDevice(r.device));
     const int64_t n = mp->dims[mp->ndims - 1];
+    LaunchTimer lt(r.plan, KIND_COMM, r.ms);   // profiling: the whole push of this level on the comm stream
     for (int dq = 0; dq < mp->world; ++dq) {
         const int q = (r.rank + dq) % mp->world;
         bool any = false;
@@ -208,22 +251,29 @@ static int push_halos(nddwt_mplan *mp, RankCtx &r, const PushSrc *srcs, int nsrc
             const std::vector<Run> runs = halo_runs(n, mp->start, mp->count, q, which, below, above);
             for (const Run &run : runs) {
                 if (run.owner != r.rank) continue;
-                if (!any && q != r.rank) {
-                    const uint32_t fills = r.sent[(size_t)q * NCH + ch_filled];
-                    if (fills > 0) { int rc = fab_wait(mp, r, q, ch_free, r.ms, fills); if (rc) return rc; }
+                if (!any) {
+                    if (q != r.rank) {
+                        uint32_t &rounds = r.rounds[(size_t)q * NCH + ch_filled];
+                        if (rounds > 0) { int rc = fab_wait(mp, r, q, ch_free, r.ms, rounds); if (rc) return rc; }
+                        ++rounds;
+                    }
+                    NDDWT_CUDA(cudaSetDevice(r.device));
+                    int rc = fork_streams(mp, r);
+                    if (rc) return rc;
                 }
                 any = true;
                 for (int a = 0; a < nsrc; ++a) {
                     char *dst = inbox_ptr(mp, q, par, which) + (size_t)(run.off + srcs[a].slot_shift[which]) * mp->plane_bytes;
                     const char *src = srcs[a].base + (size_t)run.idx * mp->plane_bytes;
-                    NDDWT_CUDA(cudaMemcpyAsync(dst, src, (size_t)run.cnt * mp->plane_bytes, cudaMemcpyDefault, r.ms));
-                    mp->copies++;
-                    mp->copy_bytes += run.cnt * (int64_t)mp->plane_bytes;
+                    int rc = peer_copy(mp, r, dst, src, (size_t)run.cnt * mp->plane_bytes);
+                    if (rc) return rc;
                 }
             }
         }
+        if (any) { int rc = join_streams(mp, r); if (rc) return rc; }
         if (any && q != r.rank) { int rc = fab_signal(mp, r, q, ch_filled, r.ms); if (rc) return rc; }
     }
+    NDDWT_CUDA(cudaSetDevice(r.device));
     NDDWT_CUDA(cudaEventRecord(r.ev_pushed, r.ms));
     r.pushed_once = true;
     return 0;
@@ -295,6 +345,8 @@ static void release(nddwt_mplan *mp)
         if (c.arena) cudaFree(c.arena);
         if (c.cs) cudaStreamDestroy(c.cs);
         if (c.ms) cudaStreamDestroy(c.ms);
+        for (int i = 0; i < 3; ++i) { if (c.mx[i]) cudaStreamDestroy(c.mx[i]); if (c.ev_join[i]) cudaEventDestroy(c.ev_join[i]); }
+        if (c.ev_fork) cudaEventDestroy(c.ev_fork);
         if (c.ev_prod) cudaEventDestroy(c.ev_prod);
         if (c.ev_pushed) cudaEventDestroy(c.ev_pushed);
     }
@@ -346,6 +398,7 @@ static int create_common(nddwt_mplan **out, int ndims, const int64_t *dims, cons
         c.count = mp->count[c.rank];
         c.sent.assign((size_t)world * NCH, 0);
         c.expect.assign((size_t)world * NCH, 0);
+        c.rounds.assign((size_t)world * NCH, 0);
         mp->local_index[c.rank] = (int)i;
         int64_t ld[NDDWT_MAX_DIMS];
         for (int k = 0; k < ndims; ++k) ld[k] = dims[k];
@@ -403,6 +456,11 @@ static int allocate(nddwt_mplan *mp)
         NDDWT_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
         NDDWT_CUDA(cudaStreamCreateWithFlags(&c.cs, cudaStreamNonBlocking));
         NDDWT_CUDA(cudaStreamCreateWithPriority(&c.ms, cudaStreamNonBlocking, hi_prio));
+        for (int i = 0; i < 3; ++i) {
+            NDDWT_CUDA(cudaStreamCreateWithPriority(&c.mx[i], cudaStreamNonBlocking, hi_prio));
+            NDDWT_CUDA(cudaEventCreateWithFlags(&c.ev_join[i], cudaEventDisableTiming));
+        }
+        NDDWT_CUDA(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
         NDDWT_CUDA(cudaEventCreateWithFlags(&c.ev_prod, cudaEventDisableTiming));
         NDDWT_CUDA(cudaEventCreateWithFlags(&c.ev_pushed, cudaEventDisableTiming));
         NDDWT_CUDA(cudaDeviceSynchronize());
@@ -410,8 +468,333 @@ static int allocate(nddwt_mplan *mp)
     }
     NDDWT_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&mp->status_host), 64, cudaHostAllocMapped | cudaHostAllocPortable));
     memset(mp->status_host, 0, 64);
-    mp->ev.assign((size_t)mp->world * mp->world * NCH, nullptr);
-    mp->ev_recorded.assign((size_t)mp->world * mp->world * NCH, 0);
+    if (!mp->flags_mode) {
+        mp->ev.assign((size_t)mp->world * mp->world * NCH * EV_RING, nullptr);
+        mp->ev_recorded.assign((size_t)mp->world * mp->world * NCH * EV_RING, 0);
+    }
+    return 0;
+}
+
+// ---- z-chunked exchange (separable 4-D plans) ---------------------------------------------------------
+struct Chunks {
+    int C = 1;
+    std::vector<int> zb;          // chunk c covers dim-3 planes zb[c] .. zb[c+1]-1
+    size_t row_bytes = 0;         // bytes of one dim-3 plane of one hyperplane (n1 * n2 elements)
+    size_t off(int c) const { return (size_t)zb[c] * row_bytes; }
+    size_t bytes(int c) const { return (size_t)(zb[c + 1] - zb[c]) * row_bytes; }
+    ZRange range(int c) const { ZRange z; z.z0 = zb[c]; z.zn = zb[c + 1] - zb[c]; return z; }
+};
+
+static Chunks make_chunks(const nddwt_mplan *mp)
+{
+    Chunks ch;
+    const int n3 = (int)mp->dims[2];
+    int C = mp->z_chunks;
+    if (C > n3 / 8) C = n3 / 8;      // a chunk must be wider than the dim-3 filter support
+    if (C < 1) C = 1;
+    ch.C = C;
+    for (int c = 0; c <= C; ++c) ch.zb.push_back((int)((int64_t)c * n3 / C));
+    ch.row_bytes = (size_t)mp->dims[0] * mp->dims[1] * mp->esize;
+    return ch;
+}
+
+// `height` hyperplanes, `width` bytes of each (one z-chunk), cut in comm_streams pieces
+static int peer_copy2d(nddwt_mplan *mp, RankCtx &r, char *dst, const char *src, size_t width, size_t height, cudaStream_t only)
+{
+    const int ns = only ? 1 : mp->comm_streams;
+    const size_t piece = ((width + ns - 1) / ns + 255) / 256 * 256;
+    for (int i = 0; i < ns; ++i) {
+        const size_t o = (size_t)i * piece;
+        if (o >= width) break;
+        const size_t n = width - o < piece ? width - o : piece;
+        cudaStream_t st = only ? only : (i == 0 ? r.ms : r.mx[i - 1]);
+        NDDWT_CUDA(cudaMemcpy2DAsync(dst + o, mp->plane_bytes, src + o, mp->plane_bytes, n, height, cudaMemcpyDefault, st));
+    }
+    if (!only) { mp->copies++; mp->copy_bytes += (int64_t)(width * height); }
+    return 0;
+}
+
+// rank r pushes chunk c of the planes of `base` its neighbours need (analysis halo shape) into their inboxes `par`
+static int push_halo_chunk(nddwt_mplan *mp, RankCtx &r, const char *base, const Chunks &ch, int c, bool first, int par)
+{
+    NDDWT_CUDA(cudaSetDevice(r.device));
+    const int64_t n = mp->dims[mp->ndims - 1];
+    const int L = mp->L_last;
+    const int64_t below = L / 2 - 1, above = L / 2;
+    const int ch_filled = CH_HALO_FILLED0 + par, ch_free = CH_HALO_FREE0 + par;
+    LaunchTimer lt(r.plan, KIND_COMM, r.ms);
+    for (int dq = 1; dq < mp->world; ++dq) {
+        const int q = (r.rank + dq) % mp->world;
+        bool any = false;
+        for (int which = 0; which < 2; ++which)
+            for (const Run &run : halo_runs(n, mp->start, mp->count, q, which, below, above)) {
+                if (run.owner != r.rank) continue;
+                if (!any) {
+                    if (first) {
+                        uint32_t &rounds = r.rounds[(size_t)q * NCH + ch_filled];
+                        if (rounds > 0) { int rc = fab_wait(mp, r, q, ch_free, r.ms, rounds); if (rc) return rc; }
+                        ++rounds;
+                    }
+                    NDDWT_CUDA(cudaSetDevice(r.device));
+                    int rc = fork_streams(mp, r);
+                    if (rc) return rc;
+                    any = true;
+                }
+                int rc = peer_copy2d(mp, r, inbox_ptr(mp, q, par, which) + (size_t)run.off * mp->plane_bytes + ch.off(c),
+                                     base + (size_t)run.idx * mp->plane_bytes + ch.off(c), ch.bytes(c), (size_t)run.cnt, nullptr);
+                if (rc) return rc;
+            }
+        if (any) {
+            int rc = join_streams(mp, r);
+            if (rc) return rc;
+            rc = fab_signal(mp, r, q, ch_filled, r.ms);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+// planes of the rank's own slab that wrap around into its own halo (few ranks, thin slabs): local copies on the compute stream
+static int self_halo_chunk(nddwt_mplan *mp, RankCtx &r, const char *base, const Chunks &ch, int c, int par, cudaStream_t cs)
+{
+    const int64_t n = mp->dims[mp->ndims - 1];
+    const int L = mp->L_last;
+    for (int which = 0; which < 2; ++which)
+        for (const Run &run : halo_runs(n, mp->start, mp->count, r.rank, which, L / 2 - 1, L / 2)) {
+            if (run.owner != r.rank) continue;
+            NDDWT_CUDA(cudaSetDevice(r.device));
+            int rc = peer_copy2d(mp, r, inbox_ptr(mp, r.rank, par, which) + (size_t)run.off * mp->plane_bytes + ch.off(c),
+                                 base + (size_t)run.idx * mp->plane_bytes + ch.off(c), ch.bytes(c), (size_t)run.cnt, cs);
+            if (rc) return rc;
+        }
+    return 0;
+}
+
+static void band_ptrs(const nddwt_mplan *mp, const RankCtx &c, char *coeffs, int level, int j, void **bands);
+
+static int dec_chunked(nddwt_mplan *mp, const void *const *x_slabs, void *const *coeff_slabs, int level,
+                       const std::vector<cudaStream_t> &cs, const Chunks &ch)
+{
+    const int nl = (int)mp->local.size(), nd = 1 << mp->ndims, L = mp->L_last, C = ch.C;
+    const int64_t below = L / 2 - 1, above = L / 2;
+    int rc = 0;
+    std::vector<const void *> a_in(x_slabs, x_slabs + nl);
+    std::vector<std::vector<void *>> bands(nl, std::vector<void *>(nd));
+    for (int j = 1; j <= level; ++j) {
+        const int par = j & 1;
+        std::vector<int> order(C);
+        for (int k = 0; k < C; ++k) order[k] = ((j - 1) + k) % C;   // chunks arrive in the order the previous level produced them
+        for (int i = 0; i < nl; ++i) {
+            RankCtx &c = mp->local[i];
+                NDDWT_CUDA(cudaSetDevice(c.device));
+            band_ptrs(mp, c, reinterpret_cast<char *>(coeff_slabs[i]), level, j, bands[i].data());
+            bands[i][0] = (j == level) ? coeff_slabs[i] : c.approx[j & 1];
+            if (j == 1) {      // x is complete: all its chunks can leave at once
+                NDDWT_CUDA(cudaSetDevice(c.device));
+                NDDWT_CUDA(cudaEventRecord(c.ev_prod, cs[i]));
+                NDDWT_CUDA(cudaStreamWaitEvent(c.ms, c.ev_prod, 0));
+                for (int k = 0; k < C; ++k) {
+                    rc = push_halo_chunk(mp, c, reinterpret_cast<const char *>(a_in[i]), ch, order[k], k == 0, par);
+                    if (rc) return rc;
+                }
+            }
+        }
+        auto P1 = [&](int k) -> int {      // last-dim pass of chunk order[k]: the only reader of the halos
+            for (int i = 0; i < nl; ++i) {
+                RankCtx &c = mp->local[i];
+                NDDWT_CUDA(cudaSetDevice(c.device));
+                for (int q : halo_sources_of(mp, c.rank, below, above)) { int r2 = fab_wait(mp, c, q, CH_HALO_FILLED0 + par, cs[i]); if (r2) return r2; }
+                int r2 = self_halo_chunk(mp, c, reinterpret_cast<const char *>(a_in[i]), ch, order[k], par, cs[i]);
+                if (r2) return r2;
+                LevelIO io;
+                io.halo_lo = inbox_ptr(mp, c.rank, par, 0);
+                io.halo_hi = inbox_ptr(mp, c.rank, par, 1);
+                r2 = fused_dec_level_part(c.plan, 1, 1, a_in[i], io, bands[i].data(), cs[i], ch.range(order[k]));
+                if (r2) return r2 > 0 ? NDDWT_ERR_ARG : r2;
+                if (k == C - 1) { r2 = free_halos(mp, c, cs[i], below, above, CH_HALO_FREE0 + par); if (r2) return r2; }
+            }
+            return 0;
+        };
+        auto P2 = [&](int k, bool first_push) -> int {   // tile pass of the lo half (incl. a_j) for chunk order[k]; a_j's chunk leaves at once
+            for (int i = 0; i < nl; ++i) {
+                RankCtx &c = mp->local[i];
+                NDDWT_CUDA(cudaSetDevice(c.device));
+                LevelIO none;
+                int r2 = fused_dec_level_part(c.plan, 1, 2, a_in[i], none, bands[i].data(), cs[i], ch.range(order[k]));
+                if (r2) return r2 > 0 ? NDDWT_ERR_ARG : r2;
+                if (j < level) {
+                    NDDWT_CUDA(cudaSetDevice(c.device));
+                    NDDWT_CUDA(cudaEventRecord(c.ev_prod, cs[i]));
+                    NDDWT_CUDA(cudaStreamWaitEvent(c.ms, c.ev_prod, 0));
+                    r2 = push_halo_chunk(mp, c, reinterpret_cast<const char *>(bands[i][0]), ch, order[k], first_push, par ^ 1);
+                    if (r2) return r2;
+                }
+            }
+            return 0;
+        };
+        // software pipeline: the tile pass of a chunk needs the last-dim pass of both neighbouring chunks
+        if ((rc = P1(0))) return rc;
+        if (C > 1 && (rc = P1(1))) return rc;
+        for (int k = 1; k < C; ++k) {
+            if (k + 1 < C && (rc = P1(k + 1))) return rc;
+            if ((rc = P2(k, k == 1))) return rc;
+        }
+        if ((rc = P2(0, C == 1))) return rc;
+        for (int i = 0; i < nl; ++i) {      // remaining detail bands (hi half), whole range, while a_j travels
+            RankCtx &c = mp->local[i];
+                NDDWT_CUDA(cudaSetDevice(c.device));
+            LevelIO none;
+            rc = fused_dec_level_part(c.plan, 1, 3, a_in[i], none, bands[i].data(), cs[i]);
+            if (rc) return rc > 0 ? NDDWT_ERR_ARG : rc;
+            c.plan->last_path = 1;
+            a_in[i] = bands[i][0];
+        }
+    }
+    return 0;
+}
+
+static int rec_chunked(nddwt_mplan *mp, const void *const *coeff_slabs, void *const *x_slabs, int level,
+                       const std::vector<cudaStream_t> &cs, const Chunks &ch)
+{
+    const int nl = (int)mp->local.size(), nd = 1 << mp->ndims, L = mp->L_last, C = ch.C;
+    const int64_t below = L / 2 - 1, above = L / 2;
+    int rc = 0;
+    std::vector<const void *> a(coeff_slabs, coeff_slabs + nl);
+    std::vector<std::vector<void *>> bands(nl, std::vector<void *>(nd));
+    auto set_bands = [&](int i, int j, const void *approx) {
+        band_ptrs(mp, mp->local[i], reinterpret_cast<char *>(const_cast<void *>(coeff_slabs[i])), level, j, bands[i].data());
+        bands[i][0] = const_cast<void *>(approx);
+    };
+    for (int i = 0; i < nl; ++i) {
+        RankCtx &c = mp->local[i];
+                NDDWT_CUDA(cudaSetDevice(c.device));
+        set_bands(i, level, a[i]);
+        rc = fused_rec_stage1(c.plan, 1, bands[i].data(), c.u_lo, c.u_hi[level & 1], cs[i], 2);
+        if (rc) return rc > 0 ? NDDWT_ERR_ARG : rc;
+    }
+    for (int j = level; j >= 1; --j) {
+        const int k2 = j & 1;
+        std::vector<void *> dst(nl);
+        std::vector<std::vector<Piece>> pieces(nl);
+        for (int i = 0; i < nl; ++i) {
+            RankCtx &c = mp->local[i];
+                NDDWT_CUDA(cudaSetDevice(c.device));
+            dst[i] = (j == 1) ? x_slabs[i] : c.approx[j & 1];
+            set_bands(i, j, a[i]);
+            pieces[i] = pieces_into(mp, c.rank, below, above);
+            NDDWT_CUDA(cudaSetDevice(c.device));
+            if (c.pushed_once) NDDWT_CUDA(cudaStreamWaitEvent(cs[i], c.ev_pushed, 0));   // the previous level's overhangs have left
+        }
+        auto adds = [&](int kc) -> int {      // add what the neighbours computed for chunk kc of my planes
+            for (int i = 0; i < nl; ++i) {
+                RankCtx &c = mp->local[i];
+                NDDWT_CUDA(cudaSetDevice(c.device));
+                std::vector<char> from(mp->world, 0);
+                for (const Piece &p : pieces[i]) if (p.src != c.rank) from[p.src] = 1;
+                for (int q = 0; q < mp->world; ++q)
+                    if (from[q]) { int r2 = fab_wait(mp, c, q, CH_STAGE_FILLED, cs[i]); if (r2) return r2; }
+                AccParams acc;
+                acc.n = 0;
+                std::vector<int> slot((size_t)c.count, -1);
+                bool fits = true;
+                for (const Piece &p : pieces[i]) {
+                    const char *s = (p.src == c.rank)
+                                        ? reinterpret_cast<const char *>(c.over[p.which]) + (size_t)p.over_off * mp->plane_bytes
+                                        : c.arena + mp->off_stage + (size_t)p.stage_off * mp->plane_bytes;
+                    for (int64_t t = 0; t < p.cnt && fits; ++t) {
+                        int &k = slot[p.idx + t];
+                        if (k < 0) {
+                            if (acc.n >= ACC_MAXP) { fits = false; break; }
+                            k = acc.n++;
+                            acc.item[k].dst = reinterpret_cast<char *>(dst[i]) + (size_t)(p.idx + t) * mp->plane_bytes + ch.off(kc);
+                            acc.item[k].ns = 0;
+                        }
+                        if (acc.item[k].ns >= ACC_MAXS) { fits = false; break; }
+                        acc.item[k].src[acc.item[k].ns++] = s + (size_t)t * mp->plane_bytes + ch.off(kc);
+                    }
+                }
+                NDDWT_CUDA(cudaSetDevice(c.device));
+                int r2 = 0;
+                if (fits) {
+                    r2 = accumulate_planes(c.plan, acc, (int64_t)(ch.bytes(kc) / mp->esize), cs[i]);
+                    if (r2) return r2;
+                } else {      // very long filters on very thin slabs: one add per overhang plane
+                    for (const Piece &p : pieces[i]) {
+                        const char *s = (p.src == c.rank)
+                                            ? reinterpret_cast<const char *>(c.over[p.which]) + (size_t)p.over_off * mp->plane_bytes
+                                            : c.arena + mp->off_stage + (size_t)p.stage_off * mp->plane_bytes;
+                        for (int64_t t = 0; t < p.cnt; ++t) {
+                            r2 = nddwt_accumulate(c.plan, reinterpret_cast<char *>(dst[i]) + (size_t)(p.idx + t) * mp->plane_bytes + ch.off(kc),
+                                                  s + (size_t)t * mp->plane_bytes + ch.off(kc), (int64_t)(ch.bytes(kc) / mp->esize), cs[i]);
+                            if (r2) return r2;
+                        }
+                    }
+                }
+                if (kc == C - 1)
+                    for (int q = 0; q < mp->world; ++q)
+                        if (from[q]) { r2 = fab_signal(mp, c, q, CH_STAGE_FREE, cs[i]); if (r2) return r2; }
+            }
+            return 0;
+        };
+        for (int k = 0; k < C; ++k) {
+            for (int i = 0; i < nl; ++i) {
+                RankCtx &c = mp->local[i];
+                NDDWT_CUDA(cudaSetDevice(c.device));
+                rc = fused_rec_stage1(c.plan, 1, bands[i].data(), c.u_lo, c.u_hi[k2], cs[i], 1, ch.range(k));
+                if (rc) return rc > 0 ? NDDWT_ERR_ARG : rc;
+                rc = fused_rec_stage2_scatter(c.plan, 1, c.u_lo, c.u_hi[k2], dst[i], c.over[0], c.over[1], cs[i], ch.range(k));
+                if (rc) return rc > 0 ? NDDWT_ERR_ARG : rc;
+                NDDWT_CUDA(cudaSetDevice(c.device));
+                NDDWT_CUDA(cudaEventRecord(c.ev_prod, cs[i]));
+                NDDWT_CUDA(cudaStreamWaitEvent(c.ms, c.ev_prod, 0));
+                LaunchTimer lt(c.plan, KIND_COMM, c.ms);
+                for (int dq = 1; dq < mp->world; ++dq) {
+                    const int q = (c.rank + dq) % mp->world;
+                    bool any = false;
+                    for (const Piece &p : pieces_into(mp, q, below, above)) {
+                        if (p.src != c.rank) continue;
+                        if (!any) {
+                            if (k == 0) {
+                                uint32_t &rounds = c.rounds[(size_t)q * NCH + CH_STAGE_FILLED];
+                                if (rounds > 0) { rc = fab_wait(mp, c, q, CH_STAGE_FREE, c.ms, rounds); if (rc) return rc; }
+                                ++rounds;
+                            }
+                            NDDWT_CUDA(cudaSetDevice(c.device));
+                            rc = fork_streams(mp, c);
+                            if (rc) return rc;
+                            any = true;
+                        }
+                        rc = peer_copy2d(mp, c, mp->peer_arena[q] + mp->off_stage + (size_t)p.stage_off * mp->plane_bytes + ch.off(k),
+                                         reinterpret_cast<const char *>(c.over[p.which]) + (size_t)p.over_off * mp->plane_bytes + ch.off(k),
+                                         ch.bytes(k), (size_t)p.cnt, nullptr);
+                        if (rc) return rc;
+                    }
+                    if (any) {
+                        rc = join_streams(mp, c);
+                        if (rc) return rc;
+                        rc = fab_signal(mp, c, q, CH_STAGE_FILLED, c.ms);
+                        if (rc) return rc;
+                    }
+                }
+                if (k == C - 1) {
+                    NDDWT_CUDA(cudaSetDevice(c.device));
+                    NDDWT_CUDA(cudaEventRecord(c.ev_pushed, c.ms));
+                    c.pushed_once = true;
+                }
+            }
+            if (k >= 1 && (rc = adds(k - 1))) return rc;
+        }
+        if (j > 1)      // detail-only half of the next level: independent of this level's result, hides the last chunk's flight
+            for (int i = 0; i < nl; ++i) {
+                RankCtx &c = mp->local[i];
+                NDDWT_CUDA(cudaSetDevice(c.device));
+                set_bands(i, j - 1, coeff_slabs[i]);
+                rc = fused_rec_stage1(c.plan, 1, bands[i].data(), c.u_lo, c.u_hi[(j - 1) & 1], cs[i], 2);
+                if (rc) return rc > 0 ? NDDWT_ERR_ARG : rc;
+            }
+        if ((rc = adds(C - 1))) return rc;
+        for (int i = 0; i < nl; ++i) { a[i] = dst[i]; mp->local[i].plan->last_path = 1; }
+    }
     return 0;
 }
 
@@ -574,6 +957,8 @@ int nddwt_mplan_set_dilations(nddwt_mplan *mp, const int *dil, int nlevels)
             for (int i = 0; i < 2; ++i) { cudaFree(c.approx[i]); cudaFree(c.u_hi[i]); cudaFree(c.over[i]); c.approx[i] = c.u_hi[i] = c.over[i] = nullptr; }
             cudaFree(c.u_lo); cudaFree(c.arena); c.u_lo = nullptr; c.arena = nullptr;
             cudaStreamDestroy(c.cs); cudaStreamDestroy(c.ms); c.cs = c.ms = nullptr;
+            for (int i = 0; i < 3; ++i) { cudaStreamDestroy(c.mx[i]); cudaEventDestroy(c.ev_join[i]); c.mx[i] = nullptr; c.ev_join[i] = nullptr; }
+            cudaEventDestroy(c.ev_fork); c.ev_fork = nullptr;
             cudaEventDestroy(c.ev_prod); cudaEventDestroy(c.ev_pushed); c.ev_prod = c.ev_pushed = nullptr;
         }
         for (cudaEvent_t e : mp->ev) if (e) cudaEventDestroy(e);
@@ -587,6 +972,16 @@ int nddwt_mplan_set_dilations(nddwt_mplan *mp, const int *dil, int nlevels)
 int nddwt_mplan_set_param(nddwt_mplan *mp, const char *name, int64_t value)
 {
     if (!mp || !name) { set_error("null argument"); return NDDWT_ERR_ARG; }
+    if (strcmp(name, "z_chunks") == 0) {
+        if (value < 1 || value > 64) { set_error("z_chunks must be 1..64"); return NDDWT_ERR_ARG; }
+        mp->z_chunks = (int)value;
+        return 0;
+    }
+    if (strcmp(name, "comm_streams") == 0) {
+        if (value < 1 || value > 4) { set_error("comm_streams must be 1..4"); return NDDWT_ERR_ARG; }
+        mp->comm_streams = (int)value;
+        return 0;
+    }
     for (RankCtx &c : mp->local) { int rc = nddwt_plan_set_param(c.plan, name, value); if (rc) return rc; }
     return 0;
 }
@@ -609,6 +1004,19 @@ int64_t nddwt_mplan_launch_count(const nddwt_mplan *mp)
 }
 
 int64_t nddwt_mplan_halo_bytes(const nddwt_mplan *mp) { return mp ? mp->copy_bytes : 0; }
+
+int nddwt_mplan_profile(nddwt_mplan *mp, int on)
+{
+    if (!mp) { set_error("null plan"); return NDDWT_ERR_ARG; }
+    for (RankCtx &c : mp->local) { int rc = nddwt_plan_profile(c.plan, on); if (rc) return rc; }
+    return 0;
+}
+
+int nddwt_mplan_kernel_time(nddwt_mplan *mp, int local_index, int kind, double *total_ms, int64_t *count)
+{
+    if (!mp || local_index < 0 || local_index >= (int)mp->local.size()) { set_error("bad argument"); return NDDWT_ERR_ARG; }
+    return nddwt_plan_kernel_time(mp->local[local_index].plan, kind, total_ms, count);
+}
 int nddwt_mplan_wait_timeouts(const nddwt_mplan *mp) { return (mp && mp->status_host) ? (int)*(volatile uint32_t *)mp->status_host : 0; }
 
 int nddwt_mplan_sync(nddwt_mplan *mp)
@@ -617,6 +1025,7 @@ int nddwt_mplan_sync(nddwt_mplan *mp)
     for (RankCtx &c : mp->local) {
         NDDWT_CUDA(cudaSetDevice(c.device));
         NDDWT_CUDA(cudaStreamSynchronize(c.ms));
+        for (int i = 0; i < 3; ++i) NDDWT_CUDA(cudaStreamSynchronize(c.mx[i]));
         NDDWT_CUDA(cudaStreamSynchronize(c.cs));
     }
     if (nddwt_mplan_wait_timeouts(mp) > 0) { set_error("a peer flag wait timed out (a rank did not take part in the call?)"); return NDDWT_ERR_CUDA; }
@@ -641,6 +1050,10 @@ int nddwt_mplan_dec(nddwt_mplan *mp, const void *const *x_slabs, void *const *co
     std::vector<cudaStream_t> cs(nl);
     for (int i = 0; i < nl; ++i) cs[i] = streams ? reinterpret_cast<cudaStream_t>(streams[i]) : mp->local[i].cs;   // a NULL entry is the legacy default stream
     if (mp->world == 1) return nddwt_dec(mp->local[0].plan, x_slabs[0], coeff_slabs[0], level, cs[0]);
+    if (mp->separable) {
+        const Chunks ch = make_chunks(mp);
+        if (ch.C > 1) return dec_chunked(mp, x_slabs, coeff_slabs, level, cs, ch);
+    }
     std::vector<const void *> a_in(x_slabs, x_slabs + nl);
     for (int j = 1; j <= level; ++j) {
         const int par = j & 1, dil = mp->dil[j - 1];
@@ -691,6 +1104,10 @@ int nddwt_mplan_rec(nddwt_mplan *mp, const void *const *coeff_slabs, void *const
     std::vector<cudaStream_t> cs(nl);
     for (int i = 0; i < nl; ++i) cs[i] = streams ? reinterpret_cast<cudaStream_t>(streams[i]) : mp->local[i].cs;   // a NULL entry is the legacy default stream
     if (mp->world == 1) return nddwt_rec(mp->local[0].plan, coeff_slabs[0], x_slabs[0], level, cs[0]);
+    if (mp->separable) {
+        const Chunks ch = make_chunks(mp);
+        if (ch.C > 1) return rec_chunked(mp, coeff_slabs, x_slabs, level, cs, ch);
+    }
     std::vector<const void *> a(coeff_slabs, coeff_slabs + nl);     // slot 0 = deepest approximation
     std::vector<std::vector<void *>> bands(nl, std::vector<void *>(nd));
     auto set_bands = [&](int i, int j, const void *approx) {
@@ -722,24 +1139,32 @@ int nddwt_mplan_rec(nddwt_mplan *mp, const void *const *coeff_slabs, void *const
                 NDDWT_CUDA(cudaEventRecord(c.ev_prod, cs[i]));
                 NDDWT_CUDA(cudaStreamWaitEvent(c.ms, c.ev_prod, 0));
                 // push my overhang planes to their owners' stage buffers
+                LaunchTimer lt(c.plan, KIND_COMM, c.ms);
                 for (int dq = 1; dq < mp->world; ++dq) {
                     const int q = (c.rank + dq) % mp->world;
                     bool any = false;
                     for (const Piece &p : pieces_into(mp, q, below, above)) {
                         if (p.src != c.rank) continue;
                         if (!any) {
-                            const uint32_t fills = c.sent[(size_t)q * NCH + CH_STAGE_FILLED];
-                            if (fills > 0) { rc = fab_wait(mp, c, q, CH_STAGE_FREE, c.ms, fills); if (rc) return rc; }
+                            uint32_t &rounds = c.rounds[(size_t)q * NCH + CH_STAGE_FILLED];
+                            if (rounds > 0) { rc = fab_wait(mp, c, q, CH_STAGE_FREE, c.ms, rounds); if (rc) return rc; }
+                            ++rounds;
+                            NDDWT_CUDA(cudaSetDevice(c.device));
+                            rc = fork_streams(mp, c);
+                            if (rc) return rc;
                             any = true;
                         }
                         char *d = mp->peer_arena[q] + mp->off_stage + (size_t)p.stage_off * mp->plane_bytes;
                         const char *s = reinterpret_cast<const char *>(c.over[p.which]) + (size_t)p.over_off * mp->plane_bytes;
-                        NDDWT_CUDA(cudaSetDevice(c.device));
-                        NDDWT_CUDA(cudaMemcpyAsync(d, s, (size_t)p.cnt * mp->plane_bytes, cudaMemcpyDefault, c.ms));
-                        mp->copies++;
-                        mp->copy_bytes += p.cnt * (int64_t)mp->plane_bytes;
+                        rc = peer_copy(mp, c, d, s, (size_t)p.cnt * mp->plane_bytes);
+                        if (rc) return rc;
                     }
-                    if (any) { rc = fab_signal(mp, c, q, CH_STAGE_FILLED, c.ms); if (rc) return rc; }
+                    if (any) {
+                        rc = join_streams(mp, c);
+                        if (rc) return rc;
+                        rc = fab_signal(mp, c, q, CH_STAGE_FILLED, c.ms);
+                        if (rc) return rc;
+                    }
                 }
                 NDDWT_CUDA(cudaSetDevice(c.device));
                 NDDWT_CUDA(cudaEventRecord(c.ev_pushed, c.ms));
@@ -759,13 +1184,40 @@ int nddwt_mplan_rec(nddwt_mplan *mp, const void *const *coeff_slabs, void *const
                 for (const Piece &p : pieces) if (p.src != c.rank) from[p.src] = 1;
                 for (int q = 0; q < mp->world; ++q)
                     if (from[q]) { rc = fab_wait(mp, c, q, CH_STAGE_FILLED, cs[i]); if (rc) return rc; }
+                // every local plane is read and written once, whatever number of overhangs lands on it
+                AccParams acc;
+                acc.n = 0;
+                bool fits = true;
+                std::vector<int> slot((size_t)c.count, -1);
                 for (const Piece &p : pieces) {
-                    char *d = reinterpret_cast<char *>(dst[i]) + (size_t)p.idx * mp->plane_bytes;
                     const char *s = (p.src == c.rank)
                                         ? reinterpret_cast<const char *>(c.over[p.which]) + (size_t)p.over_off * mp->plane_bytes
                                         : c.arena + mp->off_stage + (size_t)p.stage_off * mp->plane_bytes;
-                    rc = nddwt_accumulate(c.plan, d, s, p.cnt * mp->plane_elems, cs[i]);
+                    for (int64_t t = 0; t < p.cnt && fits; ++t) {
+                        int &k = slot[p.idx + t];
+                        if (k < 0) {
+                            if (acc.n >= ACC_MAXP) { fits = false; break; }
+                            k = acc.n++;
+                            acc.item[k].dst = reinterpret_cast<char *>(dst[i]) + (size_t)(p.idx + t) * mp->plane_bytes;
+                            acc.item[k].ns = 0;
+                        }
+                        if (acc.item[k].ns >= ACC_MAXS) { fits = false; break; }
+                        acc.item[k].src[acc.item[k].ns++] = s + (size_t)t * mp->plane_bytes;
+                    }
+                }
+                if (fits) {
+                    NDDWT_CUDA(cudaSetDevice(c.device));
+                    rc = accumulate_planes(c.plan, acc, mp->plane_elems, cs[i]);
                     if (rc) return rc;
+                } else {
+                    for (const Piece &p : pieces) {
+                        char *d = reinterpret_cast<char *>(dst[i]) + (size_t)p.idx * mp->plane_bytes;
+                        const char *s = (p.src == c.rank)
+                                            ? reinterpret_cast<const char *>(c.over[p.which]) + (size_t)p.over_off * mp->plane_bytes
+                                            : c.arena + mp->off_stage + (size_t)p.stage_off * mp->plane_bytes;
+                        rc = nddwt_accumulate(c.plan, d, s, p.cnt * mp->plane_elems, cs[i]);
+                        if (rc) return rc;
+                    }
                 }
                 for (int q = 0; q < mp->world; ++q)
                     if (from[q]) { rc = fab_signal(mp, c, q, CH_STAGE_FREE, cs[i]); if (rc) return rc; }

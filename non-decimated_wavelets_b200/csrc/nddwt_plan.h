@@ -67,6 +67,12 @@ struct LevelIO {
     const void *halo_hi = nullptr;   // planes above
 };
 
+// dim-3 sub-range of a 4-D level (zn == 0: everything).  The multi-GPU plan issues the parts of a level per
+// z-chunk so that the halo planes of one chunk travel while the next chunk computes (nddwt_multi.cu).
+struct ZRange {
+    int z0 = 0, zn = 0;
+};
+
 // ---- generic separable kernels (nddwt_generic.cu) ----
 int generic_dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io,
                       void *const *out_bands, cudaStream_t s);
@@ -81,9 +87,9 @@ int fused_dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io,
                     void *const *out_bands, cudaStream_t s);
 int fused_rec_level(nddwt_plan *p, int dil, const void *const *in_bands, void *a_out, cudaStream_t s);
 int fused_rec_stage1(nddwt_plan *p, int dil, const void *const *in_bands, void *u_lo, void *u_hi, cudaStream_t s,
-                     int part = 0);
+                     int part = 0, const ZRange &zr = ZRange());
 int fused_dec_level_part(nddwt_plan *p, int dil, int part, const void *a_in, const LevelIO &io,
-                         void *const *out_bands, cudaStream_t s);
+                         void *const *out_bands, cudaStream_t s, const ZRange &zr = ZRange());
 int fused_rec_stage2(nddwt_plan *p, int dil, const void *u_lo, const void *u_hi, const LevelIO &io, void *a_out,
                      cudaStream_t s);
 
@@ -93,12 +99,17 @@ int fused2d_rec_level(nddwt_plan *p, int dil, const void *const *in_bands, void 
 int fused1d_transform(nddwt_plan *p, bool rec, const void *in, void *out, int level, cudaStream_t s);
 bool fused_is_separable(const nddwt_plan *p);
 int fused_rec_stage2_scatter(nddwt_plan *p, int dil, const void *u_lo, const void *u_hi, void *out, void *over_lo,
-                             void *over_hi, cudaStream_t s);
+                             void *over_hi, cudaStream_t s, const ZRange &zr = ZRange());
 int accumulate_elems(nddwt_plan *p, void *dst, const void *src, int64_t nelem, cudaStream_t s);
+// several "plane += planes" in one launch (multi-GPU synthesis exchange)
+constexpr int ACC_MAXS = 8, ACC_MAXP = 32;   // kernel parameter block stays under 4 KB
+struct AccItem { void *dst; const void *src[ACC_MAXS]; int ns; };
+struct AccParams { AccItem item[ACC_MAXP]; int n; };
+int accumulate_planes(nddwt_plan *p, const AccParams &prm, int64_t plane_elems, cudaStream_t s);
 int ensure_scratch(nddwt_plan *p);
 
 // kernel kinds for nddwt_plan_kernel_time
-enum { KIND_DEC3 = 0, KIND_REC3 = 1, KIND_DEC_LAST = 2, KIND_REC_LAST = 3, KIND_GENERIC = 4, KIND_COUNT = 5 };
+enum { KIND_DEC3 = 0, KIND_REC3 = 1, KIND_DEC_LAST = 2, KIND_REC_LAST = 3, KIND_GENERIC = 4, KIND_COMM = 5, KIND_COUNT = 6 };
 
 // RAII event bracket: records (kind, e0, e1) around a launch when profiling is on
 struct LaunchTimer {

@@ -31,7 +31,8 @@ def main():
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, pg_options=opts)
     worst = 0.0
     cases = [((32, 24, 16, 16), "db4", 3, 0), ((32, 24, 16, 4 * world), "db4", 2, 1), ((64, 32, 24), "db4", 2, 0),
-             ((40, 20, 12, 2 * world + 1), "db2", 2, 0), ((32, 16, 8, 3 * world), "db1", 2, 1)]
+             ((40, 20, 12, 2 * world + 1), "db2", 2, 0), ((32, 16, 8, 3 * world), "db1", 2, 1),
+             ((32, 16, 32, 4 * world), "db4", 3, 0)]          # dim 3 long enough for the z-chunked (pipelined) exchange
     for sizes, wname, level, l2 in cases:
         d = len(sizes)
         wn = [wname] * d

@@ -60,6 +60,8 @@ CASES = [
     ((48, 40), "db3", 2, 0, 3),                # 2-D slabs
     ((4000,), "db4", 3, 1, 4),                 # 1-D slabs
     ((32, 24, 16, 8), "db4", 2, 0, 8),         # one plane per rank: every halo plane from a different rank
+    ((32, 16, 40, 12), "db4", 3, 0, 3),        # dim 3 long enough for 4 z-chunks: the pipelined (chunked) exchange
+    ((32, 16, 36, 9), "db3", 2, 1, 4),         # chunked, ragged slabs 3/2/2/2, halo wider than the slabs
 ]
 
 
@@ -73,6 +75,17 @@ def test_emulated_ranks_whole_schedule_vs_oracle(sizes, wname, level, l2, world)
     assert orc.rel_l2(xc, orc.rec_direct(c.astype(np.complex128), wname, bool(l2))) <= 1e-5
     if len(sizes) == 4 and isinstance(wname, str):
         assert tr.plan.separable            # the overlapped scatter schedule was the one tested
+
+
+@pytest.mark.parametrize("zc", [1, 3, 5])
+def test_emulated_ranks_chunk_counts(zc):
+    """The z-chunk count of the pipelined exchange is a free parameter: uneven chunk boundaries (40 planes in 3 or
+    5 chunks) and the unchunked schedule give the same answer."""
+    sizes, wname, level = (32, 16, 40, 8), "db4", 2
+    x, y, xr, c, xc, tr = _run(sizes, wname, level, 0, [0] * 4, params={"z_chunks": zc})
+    assert orc.rel_l2(y, orc.dec_direct(x.astype(np.complex128), wname, level)) <= 1e-5
+    assert orc.rel_l2(xr, x) <= 1e-5
+    assert orc.rel_l2(xc, orc.rec_direct(c.astype(np.complex128), wname, False)) <= 1e-5
 
 
 def test_emulated_ranks_generic_kernels_and_repeat_calls():
