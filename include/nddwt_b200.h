@@ -88,6 +88,16 @@ NDDWT_API int nddwt_plan_set_dilations(nddwt_plan *plan, const int *dil, int nle
  * generic separable kernels. */
 NDDWT_API int nddwt_plan_set_batch(nddwt_plan *plan, int64_t batch);
 
+/* Fused coefficient-domain shrink: the step between dec and rec of an iterative
+ * compressed-sensing loop, x <- rec(shrink(dec(x))) (README.md:2 "such as in an iterative algorithm").
+ * mode 1 = soft threshold: every later dec of this plan (any entry point: nddwt_dec, *_host, slab levels, the
+ * multi-GPU plan) applies  c <- c * max(0, 1 - t/|c|)  (real: sign(c) max(|c| - t, 0))  to the DETAIL bands as
+ * the analysis kernels store them, so the coefficient stack is written once, already thresholded -- instead
+ * of a separate pass that reads and writes all nb bands again.  thr is a table [nlevels][2^ndims]:
+ * thr[(j-1) * 2^ndims + b] is the threshold of band b of level j (j = 1 finest); entries b = 0 are ignored
+ * (the approximation band is never thresholded); levels beyond nlevels use 0.  mode 0 switches it off. */
+NDDWT_API int nddwt_plan_set_shrink(nddwt_plan *plan, int mode, const double *thr, int nlevels);
+
 /* Selects the kernel family: 0 = auto (fused kernels where an instantiation exists, generic
  * otherwise), 1 = force the generic separable kernels.  Both run on the GPU. */
 NDDWT_API int nddwt_plan_set_kernel_mode(nddwt_plan *plan, int mode);
@@ -115,6 +125,10 @@ NDDWT_API int nddwt_plan_last_synthesis_kernel(const nddwt_plan *plan);
  * x_dev: prod(dims) elements; coeffs_dev: prod(dims)*nb elements; both DEVICE pointers on the
  * plan's device.  Asynchronous on `stream` (a cudaStream_t, may be NULL).  x is never written. */
 NDDWT_API int nddwt_dec(nddwt_plan *plan, const void *x_dev, void *coeffs_dev, int level, void *stream);
+
+/* The unfused form of the shrink: applies the plan's threshold table (nddwt_plan_set_shrink) in place to the
+ * detail bands of an existing coefficient stack (one extra read + write of every thresholded band). */
+NDDWT_API int nddwt_shrink(nddwt_plan *plan, void *coeffs_dev, int level, void *stream);
 
 /* x = rec(y)          -- replaces nd_dwt_rec / nd_dwt_rec_1level (mex/nddwt.c:142-186,242-292).
  * Unlike the reference (nddwt.c:163,264-265) the coefficient stack is never modified. */
@@ -207,6 +221,7 @@ NDDWT_API int nddwt_mplan_slab(const nddwt_mplan *mplan, int rank, int64_t *star
 NDDWT_API int nddwt_mplan_is_separable(const nddwt_mplan *mplan); /* 1: overlapped scatter schedule (fused 4-D path) */
 NDDWT_API int nddwt_mplan_set_dilations(nddwt_mplan *mplan, const int *dil, int nlevels);  /* a-trous: halos (L-1)*dil */
 NDDWT_API int nddwt_mplan_set_kernel_mode(nddwt_mplan *mplan, int mode);
+NDDWT_API int nddwt_mplan_set_shrink(nddwt_mplan *mplan, int mode, const double *thr, int nlevels);   /* nddwt_plan_set_shrink on every rank */
 /* "comm_streams" (1..4, default 2): every pushed run of planes is cut in that many pieces which travel on
  * different streams / copy engines at once; other names are forwarded to the per-rank plans. */
 NDDWT_API int nddwt_mplan_set_param(nddwt_mplan *mplan, const char *name, int64_t value);

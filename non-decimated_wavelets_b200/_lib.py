@@ -18,9 +18,10 @@ ERR_ARG, ERR_WAVELET, ERR_SHORT_DIM, ERR_CUDA, ERR_NOMEM, ERR_SIZE = -1, -2, -3,
 SYMBOLS = [
     "nddwt_last_error", "nddwt_version", "nddwt_wave_filters", "nddwt_num_bands", "nddwt_infer_level",
     "nddwt_plan_create", "nddwt_plan_create_slab", "nddwt_plan_destroy", "nddwt_plan_set_dilations",
-    "nddwt_plan_set_batch", "nddwt_plan_set_kernel_mode", "nddwt_plan_set_param", "nddwt_plan_launch_count", "nddwt_plan_last_path",
+    "nddwt_plan_set_batch", "nddwt_plan_set_kernel_mode", "nddwt_plan_set_param", "nddwt_plan_set_shrink",
+    "nddwt_mplan_set_shrink", "nddwt_plan_launch_count", "nddwt_plan_last_path",
     "nddwt_plan_profile", "nddwt_plan_kernel_time", "nddwt_plan_last_synthesis_kernel",
-    "nddwt_dec", "nddwt_rec", "nddwt_dec_host", "nddwt_rec_host",
+    "nddwt_dec", "nddwt_rec", "nddwt_shrink", "nddwt_dec_host", "nddwt_rec_host",
     "nddwt_mplan_create", "nddwt_mplan_create_rank", "nddwt_mplan_export_size", "nddwt_mplan_export",
     "nddwt_mplan_import", "nddwt_mplan_destroy", "nddwt_mplan_world", "nddwt_mplan_num_local", "nddwt_mplan_slab",
     "nddwt_mplan_is_separable", "nddwt_mplan_set_dilations", "nddwt_mplan_set_kernel_mode", "nddwt_mplan_set_param",
@@ -63,6 +64,8 @@ def lib():
     L.nddwt_plan_set_batch.argtypes = [vp, c.c_int64]
     L.nddwt_plan_set_kernel_mode.argtypes = [vp, c.c_int]
     L.nddwt_plan_set_param.argtypes = [vp, c.c_char_p, c.c_int64]
+    L.nddwt_plan_set_shrink.argtypes = [vp, c.c_int, dp, c.c_int]
+    L.nddwt_mplan_set_shrink.argtypes = [vp, c.c_int, dp, c.c_int]
     L.nddwt_plan_launch_count.argtypes = [vp]
     L.nddwt_plan_launch_count.restype = c.c_int64
     L.nddwt_plan_last_path.argtypes = [vp]
@@ -71,6 +74,7 @@ def lib():
     L.nddwt_plan_kernel_time.argtypes = [vp, c.c_int, dp, c.POINTER(c.c_int64)]
     L.nddwt_dec.argtypes = [vp, vp, vp, c.c_int, vp]
     L.nddwt_rec.argtypes = [vp, vp, vp, c.c_int, vp]
+    L.nddwt_shrink.argtypes = [vp, vp, c.c_int, vp]
     L.nddwt_dec_host.argtypes = [vp, vp, vp, c.c_int]
     L.nddwt_rec_host.argtypes = [vp, vp, vp, c.c_int]
     L.nddwt_halo_planes.argtypes = [vp, c.c_int, ip, ip]
@@ -109,6 +113,17 @@ def lib():
     L.nddwt_slab_route.argtypes = [c.c_int64, c.c_int, c.c_int, c.c_int, c.c_int64, c.c_int64, i64p, c.c_int]
     _lib = L
     return L
+
+
+def _set_shrink(fn, handle, table, ndims):
+    import numpy as np
+    if table is None:
+        check(fn(handle, 0, None, 0))
+        return
+    t = np.ascontiguousarray(np.asarray(table, dtype=np.float64))
+    if t.ndim != 2 or t.shape[1] != (1 << ndims):
+        raise ValueError("threshold table must be [nlevels][2^ndims]")
+    check(fn(handle, 1, t.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), t.shape[0]))
 
 
 def slab_route(n_last, world, rank, which, below, above):
@@ -179,6 +194,10 @@ class Plan:
     def set_param(self, name, value):
         check(lib().nddwt_plan_set_param(self.handle, str(name).encode(), int(value)))
 
+    def set_shrink(self, table):
+        """table: None (off) or [nlevels][2^ndims] soft thresholds (level 1 = finest first; column 0 ignored)."""
+        _set_shrink(lib().nddwt_plan_set_shrink, self.handle, table, self.ndims)
+
     @property
     def launches(self):
         return int(lib().nddwt_plan_launch_count(self.handle))
@@ -210,6 +229,9 @@ class Plan:
 
     def rec(self, c_ptr, x_ptr, level, stream=0):
         check(lib().nddwt_rec(self.handle, c_ptr, x_ptr, level, stream))
+
+    def shrink(self, c_ptr, level, stream=0):
+        check(lib().nddwt_shrink(self.handle, c_ptr, level, stream))
 
     def dec_host(self, x_ptr, c_ptr, level):
         check(lib().nddwt_dec_host(self.handle, x_ptr, c_ptr, level))
@@ -315,6 +337,9 @@ class MultiPlan:
 
     def set_kernel_mode(self, mode):
         check(lib().nddwt_mplan_set_kernel_mode(self.handle, int(mode)))
+
+    def set_shrink(self, table):
+        _set_shrink(lib().nddwt_mplan_set_shrink, self.handle, table, self.ndims)
 
     def set_param(self, name, value):
         check(lib().nddwt_mplan_set_param(self.handle, str(name).encode(), int(value)))

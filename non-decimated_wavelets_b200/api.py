@@ -51,6 +51,10 @@ def _np_dtype_code(precision, is_complex):
     return (NDDWT_F32, np.float32) if single else (NDDWT_F64, np.float64)
 
 
+def _lib_max_levels():
+    return 16      # NDDWT_MAX_LEVELS
+
+
 _TORCH_OF = {}
 if torch is not None:
     _TORCH_OF = {NDDWT_F32: torch.float32, NDDWT_F64: torch.float64,
@@ -135,6 +139,7 @@ class _NdDwtBase:
         self.dilations = None
         self.kernel_mode = 0
         self.params = {}
+        self.shrink = None
 
     # -- plan cache (the stored-filter object on the device) ---------------------------------
     def _plan(self, is_complex, device_index, batch=1):
@@ -150,8 +155,33 @@ class _NdDwtBase:
             pl.set_kernel_mode(self.kernel_mode)
             for name, value in self.params.items():
                 pl.set_param(name, value)
+            if self.shrink is not None:
+                pl.set_shrink(self.shrink)
             self._plans[key] = pl
         return pl
+
+    def set_shrink(self, thr):
+        """Fused coefficient-domain shrink (extension; the step between dec and rec of the iterative loops the
+        reference is meant for, README.md:2): every later `dec` returns soft-thresholded DETAIL coefficients
+        (complex: c * max(0, 1 - t/|c|); real: sign(c) * max(|c| - t, 0)); the approximation band is exempt.
+        thr: None (off), a scalar (one threshold for every detail band), a sequence of J values (one per level,
+        finest first), or a table [J][2^d] (column 0 ignored)."""
+        if thr is None:
+            self.shrink = None
+        else:
+            nd = 1 << self._ndims
+            t = np.asarray(thr, dtype=np.float64)
+            if t.ndim == 0:
+                t = np.full((_lib_max_levels(), nd), float(t))
+            elif t.ndim == 1:
+                t = np.repeat(t[:, None], nd, axis=1)
+            elif t.ndim != 2 or t.shape[1] != nd:
+                raise ValueError("thresholds: scalar, [J] or [J][2^d]")
+            if np.any(t < 0):
+                raise ValueError("thresholds must be >= 0")
+            self.shrink = np.ascontiguousarray(t)
+        for pl in self._plans.values():
+            pl.set_shrink(self.shrink)
 
     def set_param(self, name, value):
         """Named integer plan parameters (nddwt_plan_set_param), e.g. 'rows_min_ctas'."""

@@ -59,7 +59,12 @@ static int dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io
         if (rc <= 0) { p->last_path = 1; return rc; }
     }
     p->last_path = 0;
-    return generic_dec_level(p, dil, a_in, io, out_bands, s);
+    int rc = generic_dec_level(p, dil, a_in, io, out_bands, s);
+    if (rc || !p->shrink_mode) return rc;
+    // no fused epilogue on this path: threshold the detail bands in place
+    const int j = p->cur_level >= 1 && p->cur_level <= NDDWT_MAX_LEVELS ? p->cur_level : 1;
+    for (int b = 1; b < (1 << p->ndims) && !rc; ++b) rc = shrink_band(p, out_bands[b], p->numel, p->shrink_thr[j - 1][b], s);
+    return rc;
 }
 
 static int rec_level(nddwt_plan *p, int dil, const void *const *in_bands, void *a_out, cudaStream_t s)
@@ -249,6 +254,24 @@ int nddwt_plan_set_batch(nddwt_plan *p, int64_t batch)
     return 0;
 }
 
+int nddwt_plan_set_shrink(nddwt_plan *p, int mode, const double *thr, int nlevels)
+{
+    if (!p || mode < 0 || mode > 1) { set_error("shrink mode must be 0 (off) or 1 (soft threshold)"); return NDDWT_ERR_ARG; }
+    const int nd = 1 << p->ndims;
+    memset(p->shrink_thr, 0, sizeof p->shrink_thr);
+    p->shrink_mode = 0;
+    if (mode == 0) return 0;
+    if (!thr || nlevels < 1 || nlevels > NDDWT_MAX_LEVELS) { set_error("bad threshold table"); return NDDWT_ERR_ARG; }
+    for (int j = 0; j < nlevels; ++j)
+        for (int b = 1; b < nd; ++b) {      // b = 0 (approximation) is exempt
+            const double t = thr[(size_t)j * nd + b];
+            if (!(t >= 0.0)) { set_error("thresholds must be >= 0"); return NDDWT_ERR_ARG; }
+            p->shrink_thr[j][b] = t;
+        }
+    p->shrink_mode = 1;
+    return 0;
+}
+
 int nddwt_plan_set_kernel_mode(nddwt_plan *p, int mode)
 {
     if (!p || mode < 0 || mode > 1) { set_error("bad kernel mode"); return NDDWT_ERR_ARG; }
@@ -339,11 +362,31 @@ int nddwt_dec(nddwt_plan *p, const void *x_dev, void *coeffs_dev, int level, voi
             if (rc) return rc;
             bands[0] = p->approx[j & 1];
         }
+        p->cur_level = j;
         rc = dec_level(p, p->dil[j - 1], a_in, io, bands, s);
         if (rc) return rc;
         a_in = bands[0];
     }
     return 0;
+}
+
+int nddwt_shrink(nddwt_plan *p, void *coeffs_dev, int level, void *stream)
+{
+    int rc = check_level(p, level);
+    if (rc) return rc;
+    if (!coeffs_dev) { set_error("null device pointer"); return NDDWT_ERR_ARG; }
+    if (!p->shrink_mode) { set_error("no threshold table: call nddwt_plan_set_shrink first"); return NDDWT_ERR_ARG; }
+    NDDWT_CUDA(cudaSetDevice(p->device));
+    const int nd = 1 << p->ndims;
+    char *c = reinterpret_cast<char *>(coeffs_dev);
+    const size_t band_bytes = (size_t)p->numel * p->esize;
+    for (int j = 1; j <= level && !rc; ++j) {
+        const int64_t start = (int64_t)(nd - 1) * (level - j);
+        for (int b = 1; b < nd && !rc; ++b)
+            rc = shrink_band(p, c + (size_t)(start + b) * band_bytes, p->numel, p->shrink_thr[j - 1][b],
+                             reinterpret_cast<cudaStream_t>(stream));
+    }
+    return rc;
 }
 
 int nddwt_rec(nddwt_plan *p, const void *coeffs_dev, void *x_dev, int level, void *stream)
@@ -455,6 +498,7 @@ int nddwt_dec_level_slab(nddwt_plan *p, int level_index, const void *a_in, const
     LevelIO io;
     io.halo_lo = halo_lo;
     io.halo_hi = halo_hi;
+    p->cur_level = level_index;
     return dec_level(p, p->dil[level_index - 1], a_in, io, out_bands, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -491,6 +535,7 @@ int nddwt_dec_level_slab_part(nddwt_plan *p, int level_index, int part, const vo
     io.halo_lo = halo_lo;
     io.halo_hi = halo_hi;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    p->cur_level = level_index;
     if (p->kernel_mode == 0) {
         rc = fused_dec_level_part(p, p->dil[level_index - 1], part, a_in, io, out_bands, s);
         if (rc <= 0) { p->last_path = 1; return rc; }

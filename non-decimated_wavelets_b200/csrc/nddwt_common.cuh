@@ -31,6 +31,24 @@ __device__ __forceinline__ double  add(double a, double b)   { return a + b; }
 __device__ __forceinline__ float2  add(float2 a, float2 b)   { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 
+// ---- soft threshold (fused coefficient shrink): real  sign(v) max(|v| - t, 0);  complex  v max(0, 1 - t/|v|).
+// t = 0 is the identity (scale exactly 1).
+// Branch-free (the analysis tile kernel sits at its register cap; control flow in its store loop spills).
+__device__ __forceinline__ float shrink1(float v, float t) { return copysignf(fmaxf(fabsf(v) - t, 0.f), v); }
+__device__ __forceinline__ double shrink1(double v, double t) { return copysign(fmax(fabs(v) - t, 0.0), v); }
+__device__ __forceinline__ float2 shrink1(float2 v, float t)
+{
+    const float m2 = fmaxf(v.x * v.x + v.y * v.y, 1e-37f);
+    const float sc = fmaxf(1.f - t * rsqrtf(m2), 0.f);
+    return make_float2(v.x * sc, v.y * sc);
+}
+__device__ __forceinline__ double2 shrink1(double2 v, double t)
+{
+    const double m2 = fmax(v.x * v.x + v.y * v.y, 1e-300);
+    const double sc = fmax(1.0 - t * rsqrt(m2), 0.0);
+    return make_double2(v.x * sc, v.y * sc);
+}
+
 // ---- taps for one dimension, passed by value in kernel parameters (constant bank) --------
 template <typename R>
 struct DimTaps {

@@ -68,8 +68,10 @@ struct Dec3Params {
     int nhyp;           // hyperplanes per input array (1 for 3-D)
     int tiles1, tiles2, zc, nchunks;
     int halo_below;     // planes held by halo_lo
+    int band0 = 0;      // band index of out[0] within the level (8 when a part-wise 4-D launch handles the hi4 half)
     int zbase = 0, zcount = 0;   // dim-3 sub-range produced by this launch (zcount 0: all n3 planes); the
                                  // ring still reads its L-1 neighbour planes around the range, periodic in n3
+    typename Elem<T>::R thr[16]; // SHR instantiations: soft threshold per output band (0 = keep)
 };
 
 __device__ __forceinline__ int wrapi(int m, int n)
@@ -165,7 +167,7 @@ struct DispatchA<T, L, PPT, L> {
                                                const int (&)[PPT], int, const T *) {}
 };
 
-template <typename T, int L, int T2, int NT, int R2, int MINB, int CWSEL = 0, int RBM = 1, int ZINC = 0>
+template <typename T, int L, int T2, int NT, int R2, int MINB, int CWSEL = 0, int RBM = 1, int ZINC = 0, int SHR = 0>
 __global__ void __launch_bounds__(NT, MINB)
 k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
 {
@@ -187,6 +189,10 @@ k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T *SA = reinterpret_cast<T *>(smem_raw);     // [2][W2][PA]   lo3 / hi3 of the haloed tile
     T *SB = SA + 2 * W2 * PA;                    // [4][W2][PB]   (b1 + 2 b3), rows still haloed
+    // fused coefficient shrink: thresholds in shared memory (indexing the parameter block with a register would
+    // force a local-memory copy of it); first read after the two barriers of the first plane
+    __shared__ typename Elem<T>::R s_thr[SHR ? 16 : 1];
+    if (SHR && threadIdx.x < 16) s_thr[threadIdx.x] = p.thr[threadIdx.x];
 
     const int tid = threadIdx.x;
     int bid = blockIdx.x;
@@ -256,6 +262,9 @@ k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
         const int64_t off = out_boff + (int64_t)z0 * s3 + (int64_t)g2 * n1 + g1;
         c_lo[k] = p.out[8 * bsel + (mm & 1) + 4 * (mm >> 1)] + off;
         c_hi[k] = p.out[8 * bsel + (mm & 1) + 4 * (mm >> 1) + 2] + off;
+        // fused coefficient shrink: the item's band index rides in the upper bits of c_rows (no extra live register);
+        // the thresholds are read from the parameter bank at the stores
+        if (SHR) c_rows[k] |= (8 * bsel + (mm & 1) + 4 * (mm >> 1)) << 8;
     }
 
     // warm-up: planes z0-HB .. z0+HA fill ring slots 0..L-1
@@ -318,7 +327,7 @@ k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
         // output ahead), so the window costs the same registers for any run length R2.
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
-            const int rows = c_rows[k];
+            const int rows = SHR ? (c_rows[k] & 0xff) : c_rows[k];
             if (rows > 0) {
                 const T *col = SB + c_src[k];
                 T w[L][CW];
@@ -346,6 +355,16 @@ k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
                         else ld_chunk<T, CW>(col + (o + L) * PB, w[o % L]);
                     }
                     if (o < rows) {
+                        if (SHR) {
+                            const typename Elem<T>::R tl = s_thr[c_rows[k] >> 8], th = s_thr[(c_rows[k] >> 8) + 2];
+#pragma unroll
+                            for (int e = 0; e < CW; ++e) {     // one element at a time: the kernel sits at its register cap
+                                lo[e] = shrink1(lo[e], tl);
+                                asm volatile("" ::: "memory");
+                                hi[e] = shrink1(hi[e], th);
+                                asm volatile("" ::: "memory");
+                            }
+                        }
                         if (CW == 1) {
                             st_stream(plo, lo[0]);
                             st_stream(phi, hi[0]);
@@ -1454,11 +1473,17 @@ static int pick_zc(int n3, int tiles, int H, int ctas_per_wave)
     return best;
 }
 
-template <typename T, int L, int T2, int NT, int R2, int MINB, int CWSEL = 0, int RBM = 1, int ZINC = 0>
+template <typename T, int L, int T2, int NT, int R2, int MINB, int CWSEL = 0, int RBM = 1, int ZINC = 0, int SHR = 0>
 static int launch_dec3_v(nddwt_plan *p, const Dec3Params<T> &base, cudaStream_t s)
 {
     using G = Geo<T, L, T2>;
     Dec3Params<T> prm = base;
+    {   // thresholds of this level's bands; prm.out[b] == nullptr marks bands this launch does not produce
+        const int j = p->cur_level >= 1 && p->cur_level <= NDDWT_MAX_LEVELS ? p->cur_level : 1;
+        const int half = prm.band0;
+        for (int b = 0; b < 16; ++b)
+            prm.thr[b] = (typename Elem<T>::R)((SHR && b + half < (1 << p->ndims)) ? p->shrink_thr[j - 1][b + half] : 0.0);
+    }
     prm.tiles1 = (prm.n1 + G::T1 - 1) / G::T1;
     prm.tiles2 = (prm.n2 + T2 - 1) / T2;
     const int batches = prm.nhyp * (prm.in[1] ? 2 : 1);
@@ -1466,7 +1491,7 @@ static int launch_dec3_v(nddwt_plan *p, const Dec3Params<T> &base, cudaStream_t 
     prm.zc = pick_zc(prm.zcount, prm.tiles1 * prm.tiles2 * batches, L - 1, 148 * MINB);
     prm.nchunks = (prm.zcount + prm.zc - 1) / prm.zc;
     prm.halo_below = (L / 2 - 1);
-    auto kern = k_dec3_fused<T, L, T2, NT, R2, MINB, CWSEL, RBM, ZINC>;
+    auto kern = k_dec3_fused<T, L, T2, NT, R2, MINB, CWSEL, RBM, ZINC, SHR>;
     NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));   // per-device attribute: set on every launch
     const FusedTaps<T, L> tp = make_taps<T, L>(p, false);
     const int64_t grid = (int64_t)prm.tiles1 * prm.tiles2 * prm.nchunks * batches;
@@ -1510,7 +1535,8 @@ static int launch_dec3_any(nddwt_plan *p, const Dec3Params<T> &prm, cudaStream_t
         }
     }
 #endif
-    // incremental plane pointer (ZINC): no integer modulo per plane in stage A
+    // incremental plane pointer (ZINC): no integer modulo per plane in stage A; SHR: soft threshold fused into the stores
+    if (p->shrink_mode) return launch_dec3_v<T, L, 16, 256, 2, 2, 0, 1, 1, 1>(p, prm, s);
     return launch_dec3_v<T, L, 16, 256, 2, 2, 0, 1, 1>(p, prm, s);
 }
 
@@ -1976,6 +2002,7 @@ static int dec4_level(nddwt_plan *p, const void *a_in, const LevelIO &io, void *
     } else {
         prm.in[0] = (part == 2) ? lo4 : hi4;
         prm.in[1] = nullptr;
+        prm.band0 = (part == 2) ? 0 : 8;
         for (int b = 0; b < 8; ++b) prm.out[b] = reinterpret_cast<T *>(out_bands[b + (part == 2 ? 0 : 8)]);
         for (int b = 8; b < 16; ++b) prm.out[b] = nullptr;
     }

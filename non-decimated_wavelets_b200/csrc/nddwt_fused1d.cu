@@ -31,6 +31,7 @@ template <typename T, int L>
 struct Taps1 {
     typename Tap1Of<T>::type lo[L];
     typename Tap1Of<T>::type hi[L];
+    typename Elem<T>::R thr[NDDWT_MAX_LEVELS];   // fused coefficient shrink: soft threshold of d_j (0 = keep), analysis only
 };
 
 // contiguous periodic copy global -> shared: one wrap computation per thread, then increments
@@ -110,7 +111,7 @@ k_dec1_cascade(const T *__restrict__ x, T *__restrict__ coeffs, int64_t n1, int6
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int64_t g = t0 + (o + r - c0);
-                if (o + r >= c0 && o + r < c0 + TILE && g < n1) band[g] = hi[r];
+                if (o + r >= c0 && o + r < c0 + TILE && g < n1) band[g] = shrink1(hi[r], tp.thr[j - 1]);
             }
         }
         __syncthreads();
@@ -189,6 +190,8 @@ static Taps1<T, L> make_taps1(const nddwt_plan *p, bool rec)
         t.lo[k] = mk1(TT(), src.d[0].lo[k]);
         t.hi[k] = mk1(TT(), src.d[0].hi[k]);
     }
+    for (int j = 0; j < NDDWT_MAX_LEVELS; ++j)
+        t.thr[j] = (typename Elem<T>::R)((!rec && p->shrink_mode) ? p->shrink_thr[j][1] : 0.0);
     return t;
 }
 

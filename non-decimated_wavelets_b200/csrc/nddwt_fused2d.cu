@@ -13,6 +13,7 @@ template <typename T, int L>
 struct Taps2 {
     typename Elem<T>::R lo[2][L];
     typename Elem<T>::R hi[2][L];
+    typename Elem<T>::R thr[4];   // fused coefficient shrink: soft threshold per subband (0 = keep), analysis only
 };
 
 __device__ __forceinline__ int wrap2(int m, int n)
@@ -67,8 +68,8 @@ k_dec2_fused(const T *__restrict__ in, T *__restrict__ o0, T *__restrict__ o1, T
         const int g1 = a1 + c, g2 = a2 + j;
         if (g1 < n1 && g2 < n2) {
             const int64_t idx = (int64_t)g2 * n1 + g1;
-            (b2 ? o2 : o0)[idx] = lo;
-            (b2 ? o3 : o1)[idx] = hi;
+            (b2 ? o2 : o0)[idx] = shrink1(lo, tp.thr[2 * b2]);
+            (b2 ? o3 : o1)[idx] = shrink1(hi, tp.thr[2 * b2 + 1]);
         }
     }
 }
@@ -130,6 +131,8 @@ static Taps2<T, L> make_taps2(const nddwt_plan *p, bool rec)
             t.lo[d][k] = (R)src.d[d].lo[k];
             t.hi[d][k] = (R)src.d[d].hi[k];
         }
+    const int j = p->cur_level >= 1 && p->cur_level <= NDDWT_MAX_LEVELS ? p->cur_level : 1;
+    for (int b = 0; b < 4; ++b) t.thr[b] = (R)((!rec && p->shrink_mode) ? p->shrink_thr[j - 1][b] : 0.0);
     return t;
 }
 

@@ -87,6 +87,13 @@ k_rec_dim(const T *__restrict__ in_lo, const T *__restrict__ in_hi, const T *__r
     }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256) k_shrink_band(T *__restrict__ band, int64_t n, typename Elem<T>::R thr)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) band[i] = shrink1(band[i], thr);
+}
+
 static inline int grid_for(int64_t total)
 {
     int64_t b = (total + 255) / 256;
@@ -205,6 +212,24 @@ static int rec_recurse(nddwt_plan *p, int k, int dil, int idx, const void *const
         case NDDWT_C128: { using T = double2; return CALL; }           \
         default: set_error("bad dtype"); return NDDWT_ERR_ARG;         \
     }
+
+template <typename T>
+static int shrink_launch(nddwt_plan *p, T *band, int64_t n, double thr, cudaStream_t s)
+{
+    {
+        LaunchTimer lt(p, KIND_GENERIC, s);
+        k_shrink_band<T><<<grid_for(n), 256, 0, s>>>(band, n, (typename Elem<T>::R)thr);
+    }
+    p->launches++;
+    NDDWT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int shrink_band(nddwt_plan *p, void *band, int64_t nelem, double thr, cudaStream_t s)
+{
+    if (thr <= 0.0) return 0;
+    NDDWT_DISPATCH(p, shrink_launch<T>(p, reinterpret_cast<T *>(band), nelem, thr, s));
+}
 
 int generic_dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io, void *const *out_bands,
                       cudaStream_t s)

@@ -589,6 +589,7 @@ static int dec_chunked(nddwt_mplan *mp, const void *const *x_slabs, void *const 
                 NDDWT_CUDA(cudaSetDevice(c.device));
             band_ptrs(mp, c, reinterpret_cast<char *>(coeff_slabs[i]), level, j, bands[i].data());
             bands[i][0] = (j == level) ? coeff_slabs[i] : c.approx[j & 1];
+            c.plan->cur_level = j;
             if (j == 1) {      // x is complete: all its chunks can leave at once
                 NDDWT_CUDA(cudaSetDevice(c.device));
                 NDDWT_CUDA(cudaEventRecord(c.ev_prod, cs[i]));
@@ -983,6 +984,13 @@ int nddwt_mplan_set_param(nddwt_mplan *mp, const char *name, int64_t value)
         return 0;
     }
     for (RankCtx &c : mp->local) { int rc = nddwt_plan_set_param(c.plan, name, value); if (rc) return rc; }
+    return 0;
+}
+
+int nddwt_mplan_set_shrink(nddwt_mplan *mp, int mode, const double *thr, int nlevels)
+{
+    if (!mp) { set_error("null plan"); return NDDWT_ERR_ARG; }
+    for (RankCtx &c : mp->local) { int rc = nddwt_plan_set_shrink(c.plan, mode, thr, nlevels); if (rc) return rc; }
     return 0;
 }
 

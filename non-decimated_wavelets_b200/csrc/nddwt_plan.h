@@ -30,6 +30,11 @@ struct nddwt_plan {
     int last_path = 0;     // 1 fused, 0 generic
     int last_rec_kernel = 0;   // synthesis tile kernel of the last 3-D/4-D fused level: 1 direct-load, 2 bulk (32-column tiles), 4 full rows
     int64_t launches = 0;
+    // fused coefficient shrink (nddwt_plan_set_shrink): soft threshold applied to the detail bands as the
+    // analysis kernels store them; thr[j-1][b] for level j, band b (b = 0, the approximation, is exempt)
+    int shrink_mode = 0;
+    double shrink_thr[NDDWT_MAX_LEVELS][1 << NDDWT_MAX_DIMS];
+    int cur_level = 1;         // level index of the level call in flight (selects the threshold row)
     int rows_min_ctas = 118;   // full-row synthesis kernel needs at least this many CTAs (nddwt_plan_set_param)
 
     // device scratch owned by the plan (allocated on first use, reused across calls)
@@ -101,6 +106,8 @@ bool fused_is_separable(const nddwt_plan *p);
 int fused_rec_stage2_scatter(nddwt_plan *p, int dil, const void *u_lo, const void *u_hi, void *out, void *over_lo,
                              void *over_hi, cudaStream_t s, const ZRange &zr = ZRange());
 int accumulate_elems(nddwt_plan *p, void *dst, const void *src, int64_t nelem, cudaStream_t s);
+// in-place soft threshold of one band (paths whose analysis kernels have no fused epilogue)
+int shrink_band(nddwt_plan *p, void *band, int64_t nelem, double thr, cudaStream_t s);
 // several "plane += planes" in one launch (multi-GPU synthesis exchange)
 constexpr int ACC_MAXS = 8, ACC_MAXP = 32;   // kernel parameter block stays under 4 KB
 struct AccItem { void *dst; const void *src[ACC_MAXS]; int ns; };

@@ -409,3 +409,25 @@ def synth(shape, dtype, seed):
     else:
         r = rng.standard_normal(shape)
     return r.astype(dt)
+
+
+def shrink_soft(y, table, ndims):
+    """Soft threshold of the DETAIL bands of a coefficient stack `y` ([sizes, nb], deepest level first): the
+    operation `nddwt_plan_set_shrink` fuses into the analysis kernels (extension; the
+    reference leaves it to the caller's iterative loop, README.md:2).  table[j-1][b]: threshold of band b of
+    level j (j = 1 finest), column 0 ignored.  Complex: c * max(0, 1 - t/|c|); real: sign(c) * max(|c| - t, 0)."""
+    nd = 1 << ndims
+    nb = y.shape[-1]
+    level = 1 + (nb - nd) // (nd - 1)
+    out = np.array(y, copy=True)
+    table = np.asarray(table, dtype=np.float64)
+    for j in range(1, level + 1):
+        start = (nd - 1) * (level - j)           # slot arithmetic of mex/nddwt.c:209-210,226
+        for b in range(1, nd):
+            t = table[j - 1][b] if j - 1 < table.shape[0] else 0.0
+            c = out[..., start + b]
+            mag = np.abs(c)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                sc = np.where(mag > t, 1.0 - t / np.where(mag > 0, mag, 1.0), 0.0)
+            out[..., start + b] = c * sc
+    return out
