@@ -179,6 +179,66 @@ def run_reference(args, wl_name, wl):
     print(json.dumps(line))
 
 
+def _level_medians(torch, y_buf, level, nd_b):
+    """median |coefficient| of one detail band per level (finest first): thresholds that zero about half of it"""
+    meds = []
+    for j in range(1, level + 1):
+        band = y_buf[(nd_b - 1) * (level - j) + nd_b - 1]
+        sample = band.reshape(-1)[:: max(1, band.numel() // (1 << 20))]
+        meds.append(float(sample.abs().median()))
+    return meds
+
+
+def iterative_loop(torch, nd, plan, xbase, y_buf, x_out, level, nb, d, iters, stream, sizes, prec, dev):
+    nd_b = 1 << d
+    out = {}
+
+    def run(pl, lv, fused, table, n):
+        xw = xbase.clone()
+        pl.set_shrink(table if fused else None)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(n + 2):
+            if it == 2:
+                e0.record()
+            pl.dec(xw.data_ptr(), y_buf.data_ptr(), lv, stream)
+            if not fused:
+                pl.set_shrink(table)
+                pl.shrink(y_buf.data_ptr(), lv, stream)
+                pl.set_shrink(None)
+            pl.rec(y_buf.data_ptr(), xw.data_ptr(), lv, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        pl.set_shrink(None)
+        nbands = nd_b + (nd_b - 1) * (lv - 1)
+        zero = float((y_buf[1:nbands].reshape(-1)[:: 997] == 0).float().mean())
+        return e0.elapsed_time(e1) / n, zero
+
+    # the bench workload itself (db4, 3 levels for cfg5)
+    plan.set_shrink(None)
+    plan.dec(xbase.data_ptr(), y_buf.data_ptr(), level, stream)
+    table = np.repeat(np.array(_level_medians(torch, y_buf, level, nd_b))[:, None], nd_b, axis=1)
+    f_ms, zf = run(plan, level, True, table, iters)
+    u_ms, _ = run(plan, level, False, table, max(10, iters // 4))
+    nvox = int(np.prod(sizes))
+    out["workload_wavelet"] = {"levels": level, "iters": iters, "fused_ms_per_iter": f_ms, "unfused_ms_per_iter": u_ms,
+                               "fused_Mvox_per_s": nvox / f_ms / 1e3, "unfused_Mvox_per_s": nvox / u_ms / 1e3,
+                               "zeroed_fraction_of_details": zf, "thresholds": "median |d_j| per level"}
+    # Haar, level 1 (harr_nddwt_2D / harr_nddwt_4D: the only level the reference's Haar classes compute correctly)
+    hcls = {2: nd.harr_nddwt_2D, 4: nd.harr_nddwt_4D}.get(d)
+    if hcls is not None:
+        h = hcls(list(sizes), "precision", prec, "compute", "gpu")
+        hp = h._plan(True, 0)
+        hp.dec(xbase.data_ptr(), y_buf.data_ptr(), 1, stream)
+        htab = np.repeat(np.array(_level_medians(torch, y_buf, 1, nd_b))[:, None], nd_b, axis=1)
+        f_ms, zf = run(hp, 1, True, htab, iters)
+        u_ms, _ = run(hp, 1, False, htab, max(10, iters // 4))
+        out["haar_level1"] = {"iters": iters, "fused_ms_per_iter": f_ms, "unfused_ms_per_iter": u_ms,
+                              "fused_Mvox_per_s": nvox / f_ms / 1e3, "unfused_Mvox_per_s": nvox / u_ms / 1e3,
+                              "zeroed_fraction_of_details": zf,
+                              "pair_frac": 2 * (1 + nd_b) * nvox * xbase.element_size() / (f_ms * 1e-3) / 1e9 / peaks()[0]}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -189,6 +249,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kernel-mode", type=int, default=0)
+    ap.add_argument("--shrink-variant", type=int, default=-1)
+    ap.add_argument("--loop", type=int, default=100,
+                    help="iterations of the iterative loop x <- rec(shrink(dec(x))) (BASELINE configs[4]: 100 pairs, Haar and db4); 0 = skip")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="N>1: halo transport (peer-memory pushes inside the library, or NCCL send/recv)")
     ap.add_argument("--no-same-workload", action="store_true", help="N>1: skip the sharded cfg5 run")
@@ -231,6 +294,8 @@ def main():
     base = torch.randn(tuple(reversed(full)) + (2,), generator=g, device=dev, dtype=tdt)
     x = torch.view_as_complex(base).permute(*reversed(range(len(full))))
     plan = obj._plan(True, 0, batch)
+    if args.shrink_variant >= 0:
+        plan.set_param("shrink_variant", args.shrink_variant)
     y_buf = torch.empty((nb,) + tuple(reversed(full)), dtype=x.dtype, device=dev)
     x_out = torch.empty(tuple(reversed(full)), dtype=x.dtype, device=dev)
     xbase = x.permute(*reversed(range(len(full))))
@@ -325,6 +390,15 @@ def main():
                 "pair_algorithmic_bytes": pair_bytes, "pair_achieved_gbs": pair_gbs, "pair_frac": pair_gbs / peak,
                 "fused": bool(plan.last_path)}
 
+    # ---- iterative loop (BASELINE configs[4]): x <- rec(shrink(dec(x))), plan and buffers reused; the soft
+    # threshold fused into the analysis stores vs a separate in-place pass over the coefficient stack
+    loop = None
+    if args.loop > 0 and d >= 2 and batch == 1:
+        try:
+            loop = iterative_loop(torch, nd, plan, xbase, y_buf, x_out, level, nb, d, args.loop, stream, sizes, prec, dev)
+        except Exception as exc:  # noqa: BLE001
+            loop = {"error": str(exc)[:200]}
+
     # ---- e2e: the same pair through the host-buffer entry points (nd_dwt_mex shape), pinned memory
     e2e = None
     if not args.no_e2e:
@@ -373,7 +447,7 @@ def main():
         "config": {"workload": wl_name, "sizes": list(sizes), "batch": batch, "wavelet": wname, "levels": level, "bands": nb,
                    "elem": dtype, "l2": "working set %.2f GB >> 126 MB L2, no flush" % ((1 + nb) * nvox * esize / 1e9),
                    "pr_rel_err": pr_err, "dec_ms": dec_ms, "rec_ms": rec_ms, "wall_ms_per_step": t_wall / args.steps * 1e3,
-                   "step_ms_min_med_max": [min(ms), float(np.median(ms)), max(ms)]},
+                   "step_ms_min_med_max": [min(ms), float(np.median(ms)), max(ms)], "iterative_loop": loop},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line))

@@ -133,6 +133,42 @@ def _time_e2e(tr, x, y, xr, level, steps, dev):
     return float(ms[0]) / steps, nbytes, float(torch.sqrt(both[0] / both[1]))
 
 
+def _time_loop(tr, plan, x, y, xr, level, iters, dev, d):
+    """x <- rec(shrink(dec(x))), `iters` times, thresholds = median |d_j| per level (agreed through rank 0)."""
+    import torch
+    import torch.distributed as dist
+    nd_b = 1 << d
+    tr.dec(x, level, out=y)
+    meds = []
+    for j in range(1, level + 1):
+        band = y[(nd_b - 1) * (level - j) + nd_b - 1].reshape(-1)
+        meds.append(band[:: max(1, band.numel() // (1 << 20))].abs().median())
+    t = torch.stack(meds).to(torch.float64)
+    dist.broadcast(t, 0)
+    table = np.repeat(t.cpu().numpy()[:, None], nd_b, axis=1)
+    plan.set_shrink(table)
+    xw = x.clone()
+    for _ in range(2):
+        tr.dec(xw, level, out=y)
+        tr.rec(y, out=xw)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        tr.dec(xw, level, out=y)
+        tr.rec(y, out=xw)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    plan.set_shrink(None)
+    zero = (y[1:].reshape(-1)[:: 997] == 0).float().mean().to(torch.float64)
+    dist.all_reduce(zero)
+    return float(ms[0]) / iters, float(zero) / dist.get_world_size()
+
+
 def _alloc(tr, level, dtype, dev, rank):
     import torch
     tdt = torch.complex64 if dtype == "complex64" else torch.complex128
@@ -279,6 +315,25 @@ def run_multi(args, wl_name, wl):
             same = {"workload": sw_name, "sizes": list(s_sizes), "ms_per_step": ms2, "value": nv2 / (ms2 * 1e-3) / 1e6,
                     "unit": "Mvoxels/s", "planes_per_gpu": "/".join(str(c) for _, c in tr2.parts),
                     "pair_frac_per_gpu": 2 * (1 + nb2) * nv2 * esize / (ms2 * 1e-3) / 1e9 / world / peak}
+            iters = int(getattr(args, "loop", 0) or 0)
+            if iters > 0 and transport == "peer":
+                # BASELINE configs[4]: 100 dec/rec pairs on 192x192x64x48, db4 and Haar, plan and buffers reused,
+                # with the soft threshold of the iterative loop fused into the analysis stores
+                lms, zf = _time_loop(tr2, plan2, x2, y2, xr2, s_level, iters, dev, len(s_sizes))
+                same["iterative_loop_db4_J3"] = {"iters": iters, "ms_per_iter": lms, "Mvox_per_s": nv2 / lms / 1e3,
+                                                 "zeroed_fraction_of_details": zf}
+                h_sizes, h_wname, h_level, h_dtype = WORKLOADS["cfg5haar"][:4]
+                tr3, plan3 = _make_transform(slab, _lib, nd, transport, h_sizes, h_wname, h_level, h_dtype, rank, world,
+                                             local_rank, dev)
+                y3 = y2[:tr3.num_bands(h_level)]
+                hms = _time_pairs(tr3, x2, y3, xr2, h_level, max(10, iters // 2), 3, dev)
+                lms, zf = _time_loop(tr3, plan3, x2, y3, xr2, h_level, iters, dev, len(h_sizes))
+                nbh = tr3.num_bands(h_level)
+                same["haar_level1"] = {"pair_ms": hms, "pair_Mvox_per_s": nv2 / hms / 1e3,
+                                       "pair_frac_per_gpu": 2 * (1 + nbh) * nv2 * esize / (hms * 1e-3) / 1e9 / world / peak,
+                                       "iterative_loop": {"iters": iters, "ms_per_iter": lms, "Mvox_per_s": nv2 / lms / 1e3,
+                                                          "zeroed_fraction_of_details": zf}}
+                del tr3, plan3
             if not args.no_e2e:
                 ms3, nbytes, e2e_err = _time_e2e(tr2, x2, y2, xr2, s_level, 3, dev)
                 e2e = {"value": nv2 / (ms3 * 1e-3) / 1e6, "unit": "Mvoxels/s", "workload": sw_name,

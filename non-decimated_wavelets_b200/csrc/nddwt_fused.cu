@@ -298,11 +298,22 @@ k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
             if (b_mask & (1 << k)) {
-                const T *row = SA + b_src[k];
+                // SHR instantiations recompute the item offsets instead of keeping them live across the march (the
+                // kernel sits at its 128-register cap and the shrink epilogue needs the room)
+                int bs = b_src[k], bd = b_dst[k];
+                if (SHR) {
+                    int it = tid + k * NT;
+                    asm volatile("" : "+r"(it));      // keeps the recomputation inside the loop (no re-hoisting)
+                    const int r = it % W2P, g = it / W2P;
+                    const int cb = g % NCB, a = g / NCB;
+                    bs = (a * W2 + r) * PA + cb * R1;
+                    bd = (2 * a * W2 + r) * PB + cb * R1;
+                }
+                const T *row = SA + bs;
                 T v[NCH * VEC];
 #pragma unroll
                 for (int j = 0; j < NCH; ++j) ld_chunk<T, VEC>(row + j * VEC, v + j * VEC);
-                T *d0 = SB + b_dst[k];
+                T *d0 = SB + bd;
                 // lo1 and hi1 together, tap loop outermost: 2 * R1 independent FFMA2 chains
                 T acc[R1], ach[R1];
 #pragma unroll
@@ -329,7 +340,14 @@ k_dec3_fused(const Dec3Params<T> p, const FusedTaps<T, L> tp)
         for (int k = 0; k < KC; ++k) {
             const int rows = SHR ? (c_rows[k] & 0xff) : c_rows[k];
             if (rows > 0) {
-                const T *col = SB + c_src[k];
+                int csrc = c_src[k];
+                if (SHR) {
+                    int it = tid + k * NT;
+                    asm volatile("" : "+r"(it));
+                    const int cp = it % CPR, rest = it / CPR;
+                    csrc = ((rest / NRUN) * W2 + (rest % NRUN) * R2) * PB + cp * CW;
+                }
+                const T *col = SB + csrc;
                 T w[L][CW];
 #pragma unroll
                 for (int j = 0; j < L; ++j) {
@@ -1447,8 +1465,8 @@ static FusedTaps<T, L> make_taps(const nddwt_plan *p, bool rec)
     for (int d = 0; d < 3; ++d)
         for (int k = 0; k < L; ++k) {
             const int dd = d < p->ndims ? d : 0;
-            t.lo[d][k] = mk_tap(typename TapOf<T>::type(), src.d[dd].lo[k]);
-            t.hi[d][k] = mk_tap(typename TapOf<T>::type(), src.d[dd].hi[k]);
+            t.lo[d][k] = mk_tap(typename TapOf<T>::type(), padded_tap(src.d[dd].lo, p->L[dd], L, k));
+            t.hi[d][k] = mk_tap(typename TapOf<T>::type(), padded_tap(src.d[dd].hi, p->L[dd], L, k));
         }
     return t;
 }
@@ -1536,7 +1554,9 @@ static int launch_dec3_any(nddwt_plan *p, const Dec3Params<T> &prm, cudaStream_t
     }
 #endif
     // incremental plane pointer (ZINC): no integer modulo per plane in stage A; SHR: soft threshold fused into the stores
-    if (p->shrink_mode) return launch_dec3_v<T, L, 16, 256, 2, 2, 0, 1, 1, 1>(p, prm, s);
+    // shrink epilogue: one-row stage-C runs keep it spill-free (two-row runs: 260 B of spills, 6.8 vs 4.4 ms on cfg5)
+    if (p->shrink_mode) return launch_dec3_v<T, L, 16, 256, 1, 2, 0, 1, 1, 1>(p, prm, s);
+    if (p->shrink_variant == 2) return launch_dec3_v<T, L, 16, 256, 1, 2, 0, 1, 1>(p, prm, s);
     return launch_dec3_v<T, L, 16, 256, 2, 2, 0, 1, 1>(p, prm, s);
 }
 
@@ -1853,15 +1873,19 @@ static int dispatch_rec3(nddwt_plan *p, int L, const void *const *in_bands, void
     }
 }
 
-static bool uniform_taps(const nddwt_plan *p)
+static bool uniform_taps(const nddwt_plan *p) { return plan_uniform_taps(p); }
+
+// tap length the fused 3-D / 4-D kernels run with (0: no instantiation): the longest filter of the plan, at most
+// db4 (the register ring); slabs (halo planes counted for the TRUE filter of the last dim) need uniform taps
+static int fused_L(const nddwt_plan *p, bool slab)
 {
-    for (int i = 1; i < p->ndims; ++i)
-        if (p->L[i] != p->L[0]) return false;
-    return true;
+    if (slab && !plan_uniform_taps(p)) return 0;
+    const int L = plan_max_taps(p);
+    if (!plan_uniform_taps(p))
+        for (int i = 0; i < p->ndims; ++i)
+            if (p->dims[i] < L) return 0;      // a padded filter longer than the dimension: generic kernels
+    return (L == 2 || L == 4 || L == 6 || L == 8) ? L : 0;
 }
-
-
-static bool uniform_taps(const nddwt_plan *p);
 // ------------------------------- 4-D path ---------------------------------------------------
 template <typename T, int L>
 static LastTaps<T, L> make_last_taps(const nddwt_plan *p, bool rec)
@@ -1870,8 +1894,8 @@ static LastTaps<T, L> make_last_taps(const nddwt_plan *p, bool rec)
     const AllTaps<double> &src = rec ? p->rec_d : p->dec_d;
     const int d = p->ndims - 1;
     for (int k = 0; k < L; ++k) {
-        t.lo[k] = mk_tap(typename TapOf<T>::type(), src.d[d].lo[k]);
-        t.hi[k] = mk_tap(typename TapOf<T>::type(), src.d[d].hi[k]);
+        t.lo[k] = mk_tap(typename TapOf<T>::type(), padded_tap(src.d[d].lo, p->L[d], L, k));
+        t.hi[k] = mk_tap(typename TapOf<T>::type(), padded_tap(src.d[d].hi, p->L[d], L, k));
     }
     return t;
 }
@@ -2062,18 +2086,18 @@ template <typename T>
 static int dispatch_dec4(nddwt_plan *p, const void *a_in, const LevelIO &io, void *const *out_bands, cudaStream_t s,
                          int part = 0, const ZRange &zr = ZRange())
 {
-    NDDWT_L_SWITCH(p->L[0], (dec4_level<T, LL>(p, a_in, io, out_bands, s, part, zr)));
+    NDDWT_L_SWITCH(plan_max_taps(p), (dec4_level<T, LL>(p, a_in, io, out_bands, s, part, zr)));
 }
 template <typename T>
 static int dispatch_rec4(nddwt_plan *p, const void *const *in_bands, void *a_out, cudaStream_t s)
 {
-    NDDWT_L_SWITCH(p->L[0], (rec4_level<T, LL>(p, in_bands, a_out, s)));
+    NDDWT_L_SWITCH(plan_max_taps(p), (rec4_level<T, LL>(p, in_bands, a_out, s)));
 }
 template <typename T>
 static int dispatch_rec4_stage1(nddwt_plan *p, const void *const *in_bands, void *u_lo, void *u_hi, cudaStream_t s,
                                 int part = 0, const ZRange &zr = ZRange())
 {
-    NDDWT_L_SWITCH(p->L[0], (rec4_stage1<T, LL>(p, in_bands, reinterpret_cast<T *>(u_lo), reinterpret_cast<T *>(u_hi), s, part, zr)));
+    NDDWT_L_SWITCH(plan_max_taps(p), (rec4_stage1<T, LL>(p, in_bands, reinterpret_cast<T *>(u_lo), reinterpret_cast<T *>(u_hi), s, part, zr)));
 }
 template <typename T>
 static int dispatch_rec_last(nddwt_plan *p, const void *u_lo, const void *u_hi, const LevelIO &io, void *a_out,
@@ -2110,7 +2134,8 @@ static bool fused_geometry_ok(const nddwt_plan *p)
 {
     if (p->ndims < 3 || p->batch != 1) return false;
     if (!fused_ranges_ok(p)) return false;
-    if (p->dims[0] < p->L[0] || p->dims[1] < p->L[1]) return false;
+    const int FL = fused_L(p, false);
+    if (FL == 0 || p->dims[0] < FL || p->dims[1] < FL) return false;
     if (p->dims[0] % (16 / (int64_t)p->esize) != 0) return false;   // 16-byte rows (vector stores, bulk copies)
     return true;
 }
@@ -2230,16 +2255,17 @@ int fused_rec_stage2(nddwt_plan *p, int dil, const void *u_lo, const void *u_hi,
 int fused_dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io, void *const *out_bands,
                     cudaStream_t s)
 {
-    if (dil != 1 || !uniform_taps(p)) return 1;
+    const int FL = fused_L(p, io.halo_lo != nullptr || io.halo_hi != nullptr);
+    if (dil != 1 || FL == 0) return 1;
     if (p->ndims == 3) {
         if (!fused_ranges_ok(p)) return 1;
-        if (p->dims[0] < p->L[0] || p->dims[1] < p->L[1]) return 1;
+        if (p->dims[0] < FL || p->dims[1] < FL) return 1;
         if (p->dims[0] % (16 / (int64_t)p->esize) != 0) return 1;   // 16-byte row alignment for the vector stores
         switch (p->dtype) {
-            case NDDWT_C64: return dispatch_dec3<float2>(p, p->L[0], a_in, io, out_bands, s);
-            case NDDWT_F32: return dispatch_dec3<float>(p, p->L[0], a_in, io, out_bands, s);
-            case NDDWT_F64: return dispatch_dec3<double>(p, p->L[0], a_in, io, out_bands, s);
-            case NDDWT_C128: return dispatch_dec3<double2>(p, p->L[0], a_in, io, out_bands, s);
+            case NDDWT_C64: return dispatch_dec3<float2>(p, FL, a_in, io, out_bands, s);
+            case NDDWT_F32: return dispatch_dec3<float>(p, FL, a_in, io, out_bands, s);
+            case NDDWT_F64: return dispatch_dec3<double>(p, FL, a_in, io, out_bands, s);
+            case NDDWT_C128: return dispatch_dec3<double2>(p, FL, a_in, io, out_bands, s);
         }
     }
     if (p->ndims == 4 && fused_geometry_ok(p)) {
@@ -2250,16 +2276,17 @@ int fused_dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io,
 
 int fused_rec_level(nddwt_plan *p, int dil, const void *const *in_bands, void *a_out, cudaStream_t s)
 {
-    if (dil != 1 || !uniform_taps(p)) return 1;
+    const int FL = fused_L(p, false);
+    if (dil != 1 || FL == 0) return 1;
     if (p->ndims == 3) {
         if (!fused_ranges_ok(p)) return 1;
-        if (p->dims[0] < p->L[0] || p->dims[1] < p->L[1]) return 1;
+        if (p->dims[0] < FL || p->dims[1] < FL) return 1;
         if (p->dims[0] % (16 / (int64_t)p->esize) != 0) return 1;
         switch (p->dtype) {
-            case NDDWT_C64: return dispatch_rec3<float2>(p, p->L[0], in_bands, a_out, s);
-            case NDDWT_F32: return dispatch_rec3<float>(p, p->L[0], in_bands, a_out, s);
-            case NDDWT_F64: return dispatch_rec3<double>(p, p->L[0], in_bands, a_out, s);
-            case NDDWT_C128: return dispatch_rec3<double2>(p, p->L[0], in_bands, a_out, s);
+            case NDDWT_C64: return dispatch_rec3<float2>(p, FL, in_bands, a_out, s);
+            case NDDWT_F32: return dispatch_rec3<float>(p, FL, in_bands, a_out, s);
+            case NDDWT_F64: return dispatch_rec3<double>(p, FL, in_bands, a_out, s);
+            case NDDWT_C128: return dispatch_rec3<double2>(p, FL, in_bands, a_out, s);
         }
     }
     if (p->ndims == 4 && fused_geometry_ok(p)) {

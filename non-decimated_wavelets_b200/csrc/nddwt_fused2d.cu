@@ -3,8 +3,8 @@
 // four subbands once; synthesis reads the four subbands once and writes the band once.
 // Replaces level_1_dec / level_1_rec of Functions/nd_dwt_2D.m:312-337 (and harr_nddwt_2D.m:250-323)
 // and nd_dwt_dec_1level / nd_dwt_rec_1level (mex/nddwt.c:98-186) for num_dims == 2.
-// Any tap length (db1..db10), any of the four element types, any (odd) sizes; same wavelet in both
-// dimensions (mixed wavelets run the generic separable kernels).
+// Any tap length (db1..db10), any of the four element types, any (odd) sizes; mixed wavelets run with the
+// longer tap length, the shorter filter zero-padded symmetrically (same phase, same result).
 #include "nddwt_plan.h"
 
 namespace nddwt {
@@ -128,8 +128,8 @@ static Taps2<T, L> make_taps2(const nddwt_plan *p, bool rec)
     const AllTaps<double> &src = rec ? p->rec_d : p->dec_d;
     for (int d = 0; d < 2; ++d)
         for (int k = 0; k < L; ++k) {
-            t.lo[d][k] = (R)src.d[d].lo[k];
-            t.hi[d][k] = (R)src.d[d].hi[k];
+            t.lo[d][k] = (R)padded_tap(src.d[d].lo, p->L[d], L, k);     // mixed wavelets: the shorter filter is zero-padded
+            t.hi[d][k] = (R)padded_tap(src.d[d].hi, p->L[d], L, k);
         }
     const int j = p->cur_level >= 1 && p->cur_level <= NDDWT_MAX_LEVELS ? p->cur_level : 1;
     for (int b = 0; b < 4; ++b) t.thr[b] = (R)((!rec && p->shrink_mode) ? p->shrink_thr[j - 1][b] : 0.0);
@@ -194,17 +194,18 @@ static int launch_rec2(nddwt_plan *p, const void *const *in_bands, void *a_out, 
 template <typename T>
 static int dispatch_dec2(nddwt_plan *p, const void *a_in, void *const *out_bands, cudaStream_t s)
 {
-    NDDWT2_L_SWITCH(p->L[0], (launch_dec2<T, LL>(p, a_in, out_bands, s)));
+    NDDWT2_L_SWITCH(plan_max_taps(p), (launch_dec2<T, LL>(p, a_in, out_bands, s)));
 }
 template <typename T>
 static int dispatch_rec2(nddwt_plan *p, const void *const *in_bands, void *a_out, cudaStream_t s)
 {
-    NDDWT2_L_SWITCH(p->L[0], (launch_rec2<T, LL>(p, in_bands, a_out, s)));
+    NDDWT2_L_SWITCH(plan_max_taps(p), (launch_rec2<T, LL>(p, in_bands, a_out, s)));
 }
 
 static bool ok2d(const nddwt_plan *p, int dil, const LevelIO *io)
 {
-    if (dil != 1 || p->ndims != 2 || p->batch != 1 || p->L[0] != p->L[1]) return false;
+    if (dil != 1 || p->ndims != 2 || p->batch != 1) return false;
+    if (p->dims[0] < plan_max_taps(p) || p->dims[1] < plan_max_taps(p)) return false;
     if (io && (io->halo_lo || io->halo_hi)) return false;      // slabs of 2-D arrays use the generic kernels
     // launch geometry: dims are ints in the kernels, grid.y = ceil(n2 / 16) must stay <= 65535
     if (p->dims[0] > 0x7fffffff - 64 || p->dims[1] > (int64_t)65535 * 16) return false;

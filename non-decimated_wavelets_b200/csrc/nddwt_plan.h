@@ -34,6 +34,7 @@ struct nddwt_plan {
     // analysis kernels store them; thr[j-1][b] for level j, band b (b = 0, the approximation, is exempt)
     int shrink_mode = 0;
     double shrink_thr[NDDWT_MAX_LEVELS][1 << NDDWT_MAX_DIMS];
+    int shrink_variant = 0;
     int cur_level = 1;         // level index of the level call in flight (selects the threshold row)
     int rows_min_ctas = 118;   // full-row synthesis kernel needs at least this many CTAs (nddwt_plan_set_param)
 
@@ -71,6 +72,27 @@ struct LevelIO {
     const void *halo_lo = nullptr;   // planes below the slab along the last dim (nullptr: periodic)
     const void *halo_hi = nullptr;   // planes above
 };
+
+// Mixed wavelets in the fused kernels: every dimension runs with the LONGEST tap length of the plan; a shorter
+// filter is zero-padded symmetrically (m = (L - L_i)/2 zeros on each side), which leaves its phase L_i/2 and
+// therefore the result unchanged: sum_k g[k] x[n - k + L_i/2] == sum_k' g'[k'] x[n - k' + L/2].
+inline int plan_max_taps(const nddwt_plan *p)
+{
+    int m = 0;
+    for (int i = 0; i < p->ndims; ++i) m = p->L[i] > m ? p->L[i] : m;
+    return m;
+}
+inline double padded_tap(const double *taps, int Li, int L, int k)
+{
+    const int m = (L - Li) / 2;
+    return (k >= m && k < m + Li) ? taps[k - m] : 0.0;
+}
+inline bool plan_uniform_taps(const nddwt_plan *p)
+{
+    for (int i = 1; i < p->ndims; ++i)
+        if (p->L[i] != p->L[0]) return false;
+    return true;
+}
 
 // dim-3 sub-range of a 4-D level (zn == 0: everything).  The multi-GPU plan issues the parts of a level per
 // z-chunk so that the halo planes of one chunk travel while the next chunk computes (nddwt_multi.cu).

@@ -93,6 +93,32 @@ def test_parity_vs_oracle(sizes, wn, level, l2, dtype):
     assert orc.rel_l2(o.rec(c), xo) <= TOL[prec]
 
 
+@pytest.mark.parametrize("sizes,wn,level,fused", [
+    ((164, 64, 40), ["db1", "db3", "db1"], 1, 1),              # Test/nddwt3D_test.m:5-7
+    ((64, 64, 20, 10), ["db1", "db3", "db1", "db1"], 1, 1),    # Test/nddwt4D_test.m:5-7
+    ((264, 264), ["db1", "db3"], 1, 1),                        # Test/nddwt2D_test.m:5-8
+    ((256, 256), ["db1", "db4"], 2, 1),                        # example_nd_dwt_2D.m:5-8
+    ((48, 40, 24), ["db4", "db2", "db3"], 2, 1),
+    ((64, 64, 20), ["db1", "db3", "db9"], 2, 0),               # db9 exceeds the register ring: generic kernels
+    ((131, 128, 30), "db3", 2, 0),                             # odd rows (no 16-byte alignment): generic kernels
+])
+def test_reference_shapes_kernel_family_and_parity(sizes, wn, level, fused):
+    """The reference's own test shapes with MIXED wavelets run the fused kernels (the shorter filters are
+    zero-padded to the longest tap length, which keeps their phase) and equal the generic kernels and the oracle."""
+    x = orc.synth(sizes, np.complex64, 8)
+    a = _obj(sizes, wn, 1, "single", kernel_mode=0)
+    b = _obj(sizes, wn, 1, "single", kernel_mode=1)
+    ya = a.dec(x, level)
+    assert a._plan(True, 0).last_path == fused
+    assert orc.rel_l2(ya, orc.dec_direct(x.astype(np.complex128), wn, level, True)) <= 1e-5
+    assert orc.rel_l2(ya, b.dec(x, level)) <= 2e-6
+    c = orc.synth(ya.shape, np.complex64, 9)
+    xa = a.rec(c)
+    assert a._plan(True, 0).last_path == fused
+    assert orc.rel_l2(xa, orc.rec_direct(c.astype(np.complex128), wn, True)) <= 1e-5
+    assert orc.rel_l2(a.rec(ya), x) <= 1e-5
+
+
 @pytest.mark.parametrize("sizes,wn,level,l2", [((64, 48, 40), "db4", 3, 0), ((129, 131), "db3", 2, 1),
                                                 ((32, 32, 24, 16), "db4", 2, 0), ((4099,), "db8", 4, 0)])
 def test_fused_equals_generic(sizes, wn, level, l2):
@@ -197,6 +223,62 @@ def test_linearity_and_shift_equivariance_full_size():
     o2 = nd.nd_dwt_3D("db4", [n, n, n], "precision", "single", "compute", "gpu", "pres_l2_norm", 1)
     y2 = o2.dec(a, 3)
     assert abs(float(torch.linalg.vector_norm(y2) / torch.linalg.vector_norm(a)) - 1) <= 1e-4
+
+
+def test_cfg3_full_size_vs_oracle():
+    """BASELINE configs[2] at full size (256^3 complex single, db4, 3 levels) against the oracle itself, not only
+    through properties: 22 bands of 16.8 M voxels, compared band by band (the oracle needs ~40 s of CPU)."""
+    n = 256
+    x = orc.synth((n, n, n), np.complex64, 13)
+    o = nd.nd_dwt_3D("db4", [n, n, n], "precision", "single", "compute", "gpu")
+    yd = o.dec(nd.to_device(x), 3)
+    assert o._plan(True, 0).last_path == 1
+    xr = nd.to_host(o.rec(yd))
+    assert orc.rel_l2(xr, x) <= 1e-5
+    y = nd.to_host(yd)
+    del yd
+    yo = orc.dec_direct(x, "db4", 3)          # numpy complex64 arithmetic (rounding ~1e-7, two decades under the tolerance)
+    assert yo.shape == y.shape
+    worst = 0.0
+    for b in range(y.shape[-1]):
+        worst = max(worst, orc.rel_l2(y[..., b], yo[..., b]))
+    assert worst <= 1e-5, worst
+
+
+@pytest.mark.parametrize("sizes,level", [((256, 24, 10, 16), 2), ((256, 40, 9, 8), 1), ((256, 17, 12, 8), 1), ((256, 32, 16, 12), 3)])
+def test_cfg4_row_length_4d(sizes, level):
+    """Rows of 256 elements (cfg4's row length): the 512-thread full-row synthesis instantiation and the
+    analysis tile kernel on several 4-D shapes (partial last row block, dim-2 wrap inside a tile, short dims)."""
+    x = orc.synth(sizes, np.complex64, 23)
+    a = _obj(sizes, "db4", 0, "single")
+    a.set_param("rows_min_ctas", 0)
+    g = _obj(sizes, "db4", 0, "single", kernel_mode=1)
+    y = a.dec(x, level)
+    assert orc.rel_l2(y, orc.dec_direct(x.astype(np.complex128), "db4", level)) <= 1e-5
+    c = orc.synth(y.shape, np.complex64, 24)
+    xa = a.rec(c)
+    assert a.synthesis_kernels() == [4]
+    assert orc.rel_l2(xa, orc.rec_direct(c.astype(np.complex128), "db4", False)) <= 1e-5
+    assert orc.rel_l2(xa, g.rec(c)) <= 2e-6
+    assert orc.rel_l2(a.rec(y), x) <= 1e-5
+
+
+def test_cfg2_batch_of_signals():
+    """BASELINE configs[1] in reduced batch (256 of the 4096 signals of 65536 samples, db8, 6 levels): the
+    batched cascade equals the oracle on sampled signals and reconstructs every signal."""
+    import torch
+    n, B, level = 65536, 256, 6
+    o = nd.nd_dwt_1D("db8", n, "precision", "single", "compute", "gpu")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    xb = torch.view_as_complex(torch.randn((B, n, 2), generator=g, device="cuda", dtype=torch.float32))   # [B][n] = column-major [n, B]
+    x = xb.permute(1, 0)
+    y = o.dec(x, level)
+    assert tuple(y.shape) == (n, B, level + 1)
+    xr = o.rec(y)
+    assert float(torch.linalg.vector_norm(xr - x) / torch.linalg.vector_norm(x)) <= 1e-5
+    for b in (0, 101, B - 1):
+        yo = orc.dec_direct(x[:, b].cpu().numpy().astype(np.complex128), "db8", level)
+        assert orc.rel_l2(y[:, b, :].cpu().numpy(), yo) <= 1e-5
 
 
 def test_dilated_atrous_mode_opt_in():
