@@ -235,6 +235,12 @@ NDDWT_API int nddwt_mplan_dec(nddwt_mplan *mplan, const void *const *x_slabs, vo
 NDDWT_API int nddwt_mplan_rec(nddwt_mplan *mplan, const void *const *coeff_slabs, void *const *x_slabs, int level,
                               void *const *streams);
 NDDWT_API int nddwt_mplan_sync(nddwt_mplan *mplan);
+/* The same two calls with whole HOST arrays (one-process plans): the shape of nd_dwt_mex(x, f, dir, level, l2)
+ * for a caller that owns every GPU of the box.  The slabs of a column-major array along its last dimension are
+ * contiguous blocks, so every GPU copies its own part of x and of every band over its own PCIe link.
+ * Synchronous. */
+NDDWT_API int nddwt_mplan_dec_host(nddwt_mplan *mplan, const void *x_host, void *coeffs_host, int level);
+NDDWT_API int nddwt_mplan_rec_host(nddwt_mplan *mplan, const void *coeffs_host, void *x_host, int level);
 NDDWT_API int64_t nddwt_mplan_launch_count(const nddwt_mplan *mplan);
 NDDWT_API int64_t nddwt_mplan_halo_bytes(const nddwt_mplan *mplan);     /* bytes pushed to peers so far (local ranks) */
 /* nddwt_plan_profile / nddwt_plan_kernel_time of one local rank's plan; kind 5 = the pushes of a level

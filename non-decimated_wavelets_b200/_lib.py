@@ -26,7 +26,7 @@ SYMBOLS = [
     "nddwt_mplan_import", "nddwt_mplan_destroy", "nddwt_mplan_world", "nddwt_mplan_num_local", "nddwt_mplan_slab",
     "nddwt_mplan_is_separable", "nddwt_mplan_set_dilations", "nddwt_mplan_set_kernel_mode", "nddwt_mplan_set_param",
     "nddwt_mplan_dec", "nddwt_mplan_rec", "nddwt_mplan_sync", "nddwt_mplan_launch_count", "nddwt_mplan_halo_bytes",
-    "nddwt_mplan_wait_timeouts", "nddwt_slab_route", "nddwt_mplan_profile", "nddwt_mplan_kernel_time",
+    "nddwt_mplan_wait_timeouts", "nddwt_slab_route", "nddwt_mplan_dec_host", "nddwt_mplan_rec_host", "nddwt_mplan_profile", "nddwt_mplan_kernel_time",
     "nddwt_halo_planes", "nddwt_dec_level_slab", "nddwt_plan_is_separable", "nddwt_dec_level_slab_part", "nddwt_rec_level_slab_stage1_part", "nddwt_rec_level_slab_stage2_scatter", "nddwt_accumulate", "nddwt_rec_level_slab_stage1", "nddwt_rec_level_slab_stage2",
 ]
 
@@ -103,6 +103,8 @@ def lib():
     L.nddwt_mplan_dec.argtypes = [vp, c.POINTER(vp), c.POINTER(vp), c.c_int, c.POINTER(vp)]
     L.nddwt_mplan_rec.argtypes = [vp, c.POINTER(vp), c.POINTER(vp), c.c_int, c.POINTER(vp)]
     L.nddwt_mplan_sync.argtypes = [vp]
+    L.nddwt_mplan_dec_host.argtypes = [vp, vp, vp, c.c_int]
+    L.nddwt_mplan_rec_host.argtypes = [vp, vp, vp, c.c_int]
     L.nddwt_mplan_launch_count.argtypes = [vp]
     L.nddwt_mplan_launch_count.restype = c.c_int64
     L.nddwt_mplan_halo_bytes.argtypes = [vp]
@@ -358,6 +360,12 @@ class MultiPlan:
 
     def sync(self):
         check(lib().nddwt_mplan_sync(self.handle))
+
+    def dec_host(self, x_ptr, c_ptr, level):
+        check(lib().nddwt_mplan_dec_host(self.handle, x_ptr, c_ptr, int(level)))
+
+    def rec_host(self, c_ptr, x_ptr, level):
+        check(lib().nddwt_mplan_rec_host(self.handle, c_ptr, x_ptr, int(level)))
 
     @property
     def launches(self):

@@ -53,6 +53,8 @@ struct RankCtx {
     void *over[2] = {nullptr, nullptr};
     cudaEvent_t ev_prod = nullptr, ev_pushed = nullptr;
     bool pushed_once = false;
+    void *host_x = nullptr, *host_c = nullptr;   // device staging of the *_host entry points (this rank's slabs)
+    size_t host_c_bytes = 0;
     std::vector<uint32_t> sent, expect;        // [world * NCH] flag sequence numbers
     std::vector<uint32_t> rounds;              // [world * NCH] exchanges started towards a peer (FREE is raised once per exchange)
 };
@@ -342,6 +344,8 @@ static void release(nddwt_mplan *mp)
         if (c.plan) nddwt_plan_destroy(c.plan);
         for (int i = 0; i < 2; ++i) { if (c.approx[i]) cudaFree(c.approx[i]); if (c.u_hi[i]) cudaFree(c.u_hi[i]); if (c.over[i]) cudaFree(c.over[i]); }
         if (c.u_lo) cudaFree(c.u_lo);
+        if (c.host_x) cudaFree(c.host_x);
+        if (c.host_c) cudaFree(c.host_c);
         if (c.arena) cudaFree(c.arena);
         if (c.cs) cudaStreamDestroy(c.cs);
         if (c.ms) cudaStreamDestroy(c.ms);
@@ -1268,6 +1272,88 @@ int nddwt_mplan_rec(nddwt_mplan *mp, const void *const *coeff_slabs, void *const
         }
     }
     return 0;
+}
+
+
+// ---- host arrays in, host arrays out (the shape of nd_dwt_mex for a MATLAB / C caller that owns all GPUs):
+// the slabs of a column-major array along its LAST dimension are contiguous, so rank r's part of x is one
+// block of the host array and its part of every band one block of that band; every GPU moves its own slabs
+// over its own PCIe link.  Needs a one-process plan (nddwt_mplan_create).
+static int host_staging(nddwt_mplan *mp, int level)
+{
+    const size_t nb = (size_t)nddwt_num_bands(mp->ndims, level);
+    for (RankCtx &c : mp->local) {
+        NDDWT_CUDA(cudaSetDevice(c.device));
+        const size_t slab = (size_t)c.count * mp->plane_bytes;
+        if (!c.host_x) NDDWT_CUDA(cudaMalloc(&c.host_x, slab));
+        if (c.host_c_bytes < slab * nb) {
+            if (c.host_c) { cudaFree(c.host_c); c.host_c = nullptr; c.host_c_bytes = 0; }
+            NDDWT_CUDA(cudaMalloc(&c.host_c, slab * nb));
+            c.host_c_bytes = slab * nb;
+        }
+    }
+    return 0;
+}
+
+int nddwt_mplan_dec_host(nddwt_mplan *mp, const void *x_host, void *coeffs_host, int level)
+{
+    if (!mp || !x_host || !coeffs_host) { set_error("null argument"); return NDDWT_ERR_ARG; }
+    if ((int)mp->local.size() != mp->world) { set_error("host entry points need a one-process plan (nddwt_mplan_create)"); return NDDWT_ERR_ARG; }
+    if (level < 1 || level > NDDWT_MAX_LEVELS) { set_error("level must be in 1..16"); return NDDWT_ERR_ARG; }
+    int rc = host_staging(mp, level);
+    if (rc) return rc;
+    const size_t nb = (size_t)nddwt_num_bands(mp->ndims, level);
+    const size_t band_bytes = (size_t)mp->dims[mp->ndims - 1] * mp->plane_bytes;
+    std::vector<const void *> xs;
+    std::vector<void *> cs;
+    for (RankCtx &c : mp->local) {
+        NDDWT_CUDA(cudaSetDevice(c.device));
+        NDDWT_CUDA(cudaMemcpyAsync(c.host_x, reinterpret_cast<const char *>(x_host) + (size_t)c.start * mp->plane_bytes,
+                                   (size_t)c.count * mp->plane_bytes, cudaMemcpyHostToDevice, c.cs));
+        xs.push_back(c.host_x);
+        cs.push_back(c.host_c);
+    }
+    rc = nddwt_mplan_dec(mp, xs.data(), cs.data(), level, nullptr);
+    if (rc) return rc;
+    for (RankCtx &c : mp->local) {
+        NDDWT_CUDA(cudaSetDevice(c.device));
+        const size_t slab = (size_t)c.count * mp->plane_bytes;
+        for (size_t b = 0; b < nb; ++b)
+            NDDWT_CUDA(cudaMemcpyAsync(reinterpret_cast<char *>(coeffs_host) + b * band_bytes + (size_t)c.start * mp->plane_bytes,
+                                       reinterpret_cast<const char *>(c.host_c) + b * slab, slab, cudaMemcpyDeviceToHost, c.cs));
+    }
+    return nddwt_mplan_sync(mp);
+}
+
+int nddwt_mplan_rec_host(nddwt_mplan *mp, const void *coeffs_host, void *x_host, int level)
+{
+    if (!mp || !x_host || !coeffs_host) { set_error("null argument"); return NDDWT_ERR_ARG; }
+    if ((int)mp->local.size() != mp->world) { set_error("host entry points need a one-process plan (nddwt_mplan_create)"); return NDDWT_ERR_ARG; }
+    if (level < 1 || level > NDDWT_MAX_LEVELS) { set_error("level must be in 1..16"); return NDDWT_ERR_ARG; }
+    int rc = host_staging(mp, level);
+    if (rc) return rc;
+    const size_t nb = (size_t)nddwt_num_bands(mp->ndims, level);
+    const size_t band_bytes = (size_t)mp->dims[mp->ndims - 1] * mp->plane_bytes;
+    std::vector<const void *> cs;
+    std::vector<void *> xs;
+    for (RankCtx &c : mp->local) {
+        NDDWT_CUDA(cudaSetDevice(c.device));
+        const size_t slab = (size_t)c.count * mp->plane_bytes;
+        for (size_t b = 0; b < nb; ++b)
+            NDDWT_CUDA(cudaMemcpyAsync(reinterpret_cast<char *>(c.host_c) + b * slab,
+                                       reinterpret_cast<const char *>(coeffs_host) + b * band_bytes + (size_t)c.start * mp->plane_bytes,
+                                       slab, cudaMemcpyHostToDevice, c.cs));
+        cs.push_back(c.host_c);
+        xs.push_back(c.host_x);
+    }
+    rc = nddwt_mplan_rec(mp, cs.data(), xs.data(), level, nullptr);
+    if (rc) return rc;
+    for (RankCtx &c : mp->local) {
+        NDDWT_CUDA(cudaSetDevice(c.device));
+        NDDWT_CUDA(cudaMemcpyAsync(reinterpret_cast<char *>(x_host) + (size_t)c.start * mp->plane_bytes, c.host_x,
+                                   (size_t)c.count * mp->plane_bytes, cudaMemcpyDeviceToHost, c.cs));
+    }
+    return nddwt_mplan_sync(mp);
 }
 
 }  // extern "C"

@@ -3,7 +3,9 @@ classdef harr_nddwt_2D
 %   obj = harr_nddwt_2D(sizes, 'pres_l2_norm',0|1, 'compute',..., 'precision',...)
 %   Interface of the reference's Functions/harr_nddwt_2D.m.
     properties
-        f_dec;
+        f_dec;          % filter descriptor (wavelet names + sizes)
+        plan_h;         % device plans built from it in the constructor: [real, complex] handles for nd_dwt_mex
+        ngpus = 1;      % extension: 'ngpus', n  splits the last dimension over n GPUs (host arrays)
         sizes;
         f_size;
         wname;

@@ -6,7 +6,9 @@ classdef nd_dwt_1D
 %   Interface of the reference's Functions/nd_dwt_1D.m; the work is done by libnddwt_b200
 %   (direct separable circular filtering, no FFT, no stored Fourier-domain filters).
     properties
-        f_dec;          % filter descriptor handed to nd_dwt_mex (wavelet names + sizes)
+        f_dec;          % filter descriptor (wavelet names + sizes)
+        plan_h;         % device plans built from it in the constructor: [real, complex] handles for nd_dwt_mex
+        ngpus = 1;      % extension: 'ngpus', n  splits the last dimension over n GPUs (host arrays)
         sizes;
         f_size;
         wname;

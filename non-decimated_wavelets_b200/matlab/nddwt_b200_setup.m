@@ -27,6 +27,7 @@ obj.wname = names;
 obj.pres_l2_norm = 0;
 obj.precision = 'double';
 obj.compute = 'mat';
+ngpus = 1;
 for k = 1:2:numel(opts)
     key = lower(opts{k});
     val = opts{k + 1};
@@ -36,6 +37,8 @@ for k = 1:2:numel(opts)
         obj.compute = val;
     elseif strcmp(key, 'precision')
         obj.precision = val;
+    elseif strcmp(key, 'ngpus')          % extension: slabs along the last dimension over several GPUs (host arrays)
+        ngpus = double(val);
     elseif any(strcmp(key, extra_keys))
         obj.(key) = val;
     else
@@ -51,6 +54,14 @@ for i = 1:ndim
         error('Dimension %d of Data is shorter than the wavelet filter being used', i);
     end
 end
-% what travels in nd_dwt_mex's second argument: names + sizes (a few bytes, not 2^d*numel complex)
+% The "stored filters": a descriptor (names + sizes, a few bytes instead of the reference's 2^d*numel complex
+% f_dec, nd_dwt_2D.m:305-308) and the device-side plans built from it ONCE, here, like the reference builds
+% f_dec in its constructor.  plan_h = [handle for real data, handle for complex data] (uint64), passed in
+% nd_dwt_mex's f position on every dec / rec; the plans own taps, scratch and -- ngpus > 1 -- the peer
+% mappings and halo inboxes of all GPUs.  They live until nd_dwt_mex('release', h) / clear mex.
 obj.f_dec = struct('wname', {names}, 'sizes', obj.sizes);
+is_single = strcmpi(obj.precision, 'single');
+obj.plan_h = [nd_dwt_mex('plan', obj.f_dec, is_single, false, obj.pres_l2_norm, ngpus), ...
+              nd_dwt_mex('plan', obj.f_dec, is_single, true, obj.pres_l2_norm, ngpus)];
+obj.ngpus = ngpus;
 end
