@@ -113,6 +113,8 @@ class _NdDwtBase:
         self.precision = "double"
         self.compute = "mat"
         self.method = "fft"
+        self.ngpus = 1
+        self.devices = None
         opts = list(zip(varargin[0::2], varargin[1::2])) + list(kwargs.items())
         for ind, (key, val) in enumerate(opts):
             k = str(key).lower()
@@ -122,6 +124,11 @@ class _NdDwtBase:
                 self.compute = str(val)
             elif k == "precision":
                 self.precision = str(val)
+            elif k == "ngpus":         # extension: slabs of the last dimension over several GPUs (host arrays)
+                self.ngpus = int(val)
+            elif k == "devices":       # extension: explicit device list for 'ngpus' (repeat an index to emulate ranks)
+                self.devices = [int(v) for v in val]
+                self.ngpus = len(self.devices)
             elif k in self._extra_options:
                 setattr(self, k, val)
             else:
@@ -182,6 +189,24 @@ class _NdDwtBase:
             self.shrink = np.ascontiguousarray(t)
         for pl in self._plans.values():
             pl.set_shrink(self.shrink)
+
+    def _mplan(self, is_complex):
+        """Multi-GPU plan of this object (one process drives `ngpus` devices; host arrays in and out)."""
+        code, _ = _np_dtype_code(self.precision, is_complex)
+        key = ("multi", code)
+        pl = self._plans.get(key)
+        if pl is None:
+            devs = self.devices if self.devices is not None else list(range(self.ngpus))
+            pl = _lib.MultiPlan(self.sizes, self.wname, code, self.pres_l2_norm, devices=devs)
+            if self.dilations is not None:
+                pl.set_dilations(self.dilations)
+            pl.set_kernel_mode(self.kernel_mode)
+            for name, value in self.params.items():
+                pl.set_param(name, value)
+            if self.shrink is not None:
+                pl.set_shrink(self.shrink)
+            self._plans[key] = pl
+        return pl
 
     def set_param(self, name, value):
         """Named integer plan parameters (nddwt_plan_set_param), e.g. 'rows_min_ctas'."""
@@ -260,7 +285,10 @@ class _NdDwtBase:
         xf = np.asfortranarray(x, dtype=npdt)
         shape = tuple(x.shape) + (self._num_bands(level),)
         y = np.empty(shape, dtype=npdt, order="F") if out is None else self._check_out(out, shape, np.dtype(npdt))
-        self._plan(is_c, 0, batch).dec_host(xf.ctypes.data, y.ctypes.data, level)
+        if self.ngpus > 1 and batch == 1:
+            self._mplan(is_c).dec_host(xf.ctypes.data, y.ctypes.data, level)
+        else:
+            self._plan(is_c, 0, batch).dec_host(xf.ctypes.data, y.ctypes.data, level)
         return y
 
     def _rec_host(self, y, out=None):
@@ -273,7 +301,10 @@ class _NdDwtBase:
         yf = np.asfortranarray(y, dtype=npdt)
         xs = tuple(y.shape[:-1])
         x = np.empty(xs, dtype=npdt, order="F") if out is None else self._check_out(out, xs, np.dtype(npdt))
-        self._plan(is_c, 0, batch).rec_host(yf.ctypes.data, x.ctypes.data, level)
+        if self.ngpus > 1 and batch == 1:
+            self._mplan(is_c).rec_host(yf.ctypes.data, x.ctypes.data, level)
+        else:
+            self._plan(is_c, 0, batch).rec_host(yf.ctypes.data, x.ctypes.data, level)
         return x
 
     def _dec_device(self, x, level):
@@ -310,7 +341,7 @@ class _NdDwtBase:
 
     def synthesis_kernels(self):
         """Synthesis tile kernel each plan of this object launched last (see Plan.last_synthesis_kernel)."""
-        return sorted(set(pl.last_synthesis_kernel for pl in self._plans.values()))
+        return sorted(set(pl.last_synthesis_kernel for pl in self._plans.values() if hasattr(pl, "last_synthesis_kernel")))
 
 
 class nd_dwt_1D(_NdDwtBase):

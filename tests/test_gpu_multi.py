@@ -123,6 +123,26 @@ def test_cfg4_row_length_schedule():
     assert orc.rel_l2(xc, orc.rec_direct(c.astype(np.complex128), wname, False)) <= 1e-5
 
 
+@pytest.mark.parametrize("sizes,wn,level,dtype", [((32, 24, 16, 12), "db4", 2, "complex64"), ((40, 20, 18), "db3", 2, "float64"),
+                                                   ((64, 30), ["db2", "db4"], 2, "complex128")])
+def test_host_arrays_through_the_multi_gpu_plan(sizes, wn, level, dtype):
+    """'ngpus' option of the object API (what the MEX gateway's 'ngpus' plans call): whole host arrays in and out,
+    every rank copies its own contiguous slab of x and of every band (nddwt_mplan_dec_host / rec_host).
+    Ranks are emulated on one GPU through the 'devices' hook when the box has fewer GPUs."""
+    n = min(_ngpus(), 3)
+    devices = list(range(n)) if n >= 2 else [0, 0, 0]
+    d = len(sizes)
+    prec = "single" if dtype in ("complex64", "float32") else "double"
+    tol = 1e-5 if prec == "single" else 1e-12
+    cls = {2: nd.nd_dwt_2D, 3: nd.nd_dwt_3D, 4: nd.nd_dwt_4D}[d]
+    o = cls(wn, list(sizes), "precision", prec, "compute", "mex", "devices", devices)
+    x = orc.synth(sizes, dtype, 4)
+    y = o.dec(x, level)
+    wide = np.complex128 if np.iscomplexobj(x) else np.float64
+    assert orc.rel_l2(y, orc.dec_direct(x.astype(wide), wn, level)) <= tol
+    assert orc.rel_l2(o.rec(y), x) <= tol
+
+
 def _ngpus():
     import torch
     return torch.cuda.device_count()
