@@ -249,8 +249,6 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kernel-mode", type=int, default=0)
-    ap.add_argument("--shrink-variant", type=int, default=-1)
-    ap.add_argument("--rows-variant", type=int, default=-1)
     ap.add_argument("--loop", type=int, default=100,
                     help="iterations of the iterative loop x <- rec(shrink(dec(x))) (BASELINE configs[4]: 100 pairs, Haar and db4); 0 = skip")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
@@ -295,10 +293,6 @@ def main():
     base = torch.randn(tuple(reversed(full)) + (2,), generator=g, device=dev, dtype=tdt)
     x = torch.view_as_complex(base).permute(*reversed(range(len(full))))
     plan = obj._plan(True, 0, batch)
-    if args.shrink_variant >= 0:
-        plan.set_param("shrink_variant", args.shrink_variant)
-    if args.rows_variant >= 0:
-        plan.set_param("rows_variant", args.rows_variant)
     y_buf = torch.empty((nb,) + tuple(reversed(full)), dtype=x.dtype, device=dev)
     x_out = torch.empty(tuple(reversed(full)), dtype=x.dtype, device=dev)
     xbase = x.permute(*reversed(range(len(full))))

@@ -287,8 +287,6 @@ int nddwt_plan_set_param(nddwt_plan *p, const char *name, int64_t value)
         p->rows_min_ctas = (int)value;
         return 0;
     }
-    if (strcmp(name, "shrink_variant") == 0) { p->shrink_variant = (int)value; return 0; }
-    if (strcmp(name, "rows_variant") == 0) { p->rows_variant = (int)value; return 0; }
     set_error(std::string("unknown plan parameter: ") + name);
     return NDDWT_ERR_ARG;
 }

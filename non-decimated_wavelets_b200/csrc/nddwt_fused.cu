@@ -1301,249 +1301,6 @@ k_rec3_rows(const Rec3Params<T> p, const FusedTaps<T, L> tp, const RowsGeo g)
 
 
 // ---------------------------------------------------------------------------------------------
-// Full-row synthesis kernel, PAIRED form (rows of at most NT/2 elements): the (b1 = 0, 1) groups of one b3 are
-// processed TOGETHER -- half of the threads per group, one column each over the FULL tile height -- so that
-//   * stage RA reads every staged element exactly once (15 window rows per 8 outputs instead of 11 per 4:
-//     -32 % of its shared-memory wavefronts; the round-2 profile puts the kernel at 63 % of the shared-memory
-//     pipe with "wait" / "short scoreboard" on top) and still keeps every warp busy;
-//   * a plane costs 4 CTA barriers instead of 5;
-//   * the staging ring holds 4 stages (stage = group, parity = plane parity): a stage is refilled right after its
-//     pair has been consumed, one whole pair + RB + RC ahead of its next use.  The room comes from SU holding one
-//     pair ([2][T2][pu]) and SV one b3 ([T2][pv]): stage RC runs in two halves (lo3 taps after b3 = 0, hi3 taps
-//     and the store after b3 = 1).
-template <typename T, int L, int VEC, int U, int HALF>
-__device__ __forceinline__ void rec_stage_c_half(T (&acc)[L][VEC], const T (&v)[VEC], const typename TapOf<T>::type *g,
-                                                 T *dst, bool store)
-{
-#pragma unroll
-    for (int k = 0; k < L; ++k)
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) macp(acc[(U - k + L) % L][e], g[k], v[e]);
-    if (HALF == 1) {
-        if (store) {
-            union { uint4 q; T t[VEC]; } a;
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) a.t[e] = acc[(U + 1) % L][e];
-            __stcs(reinterpret_cast<uint4 *>(dst), a.q);
-        }
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) acc[(U + 1) % L][e] = zero_of(T());
-    }
-}
-template <typename T, int L, int VEC, int U, int HALF>
-struct DispatchCH {
-    __device__ __forceinline__ static void run(int u, T (&acc)[L][VEC], const T (&v)[VEC], const typename TapOf<T>::type *g,
-                                               T *dst, bool store)
-    {
-        if (u == U) rec_stage_c_half<T, L, VEC, U, HALF>(acc, v, g, dst, store);
-        else DispatchCH<T, L, VEC, U + 1, HALF>::run(u, acc, v, g, dst, store);
-    }
-};
-template <typename T, int L, int VEC, int HALF>
-struct DispatchCH<T, L, VEC, L, HALF> {
-    __device__ __forceinline__ static void run(int, T (&)[L][VEC], const T (&)[VEC], const typename TapOf<T>::type *, T *, bool) {}
-};
-
-template <typename T, int L, int T2, int NT, int KC, int N1>
-__global__ void __launch_bounds__(NT, 1)
-k_rec3_rows2(const Rec3Params<T> p, const FusedTaps<T, L> tp, const RowsGeo g)
-{
-    constexpr int VEC = 16 / (int)sizeof(T);
-    constexpr int HB = L / 2, HA = L / 2 - 1, W2 = T2 + L - 1, NSTG = 4;
-    constexpr int R1B = 2 * VEC, NCHB = (R1B + L - 1 + VEC - 1) / VEC;
-    static_assert(sizeof(T) == 8 && T2 % 2 == 0, "8-byte elements, even tile height");
-
-    const int n1 = N1 ? N1 : p.n1;
-    const int pu = N1 ? rows_pu<T, L>(N1) : g.pu;
-    const int pv = N1 ? rows_pv<T>(N1) : g.pv;
-    const int stage_elems = 2 * W2 * n1;
-
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    T *STG = reinterpret_cast<T *>(smem_raw);                    // [4][2][W2][n1]   stage q = group q of the plane in flight
-    T *SU = STG + (size_t)NSTG * stage_elems;                     // [2][T2][pu]      the pair (b1 = 0, 1) of the current b3
-    T *SV = SU + 2 * T2 * pu;                                     // [T2][pv]         the current b3, dims 1,2 synthesised
-    uint64_t *bar = reinterpret_cast<uint64_t *>(SV + T2 * pv);
-
-    const int tid = threadIdx.x;
-    int bid = blockIdx.x;
-    const int t2 = bid % p.tiles2;
-    bid /= p.tiles2;
-    const int chunk = bid % p.nchunks;
-    const int batch = bid / p.nchunks;
-    const int a2 = t2 * T2;
-    const int z0 = p.zbase + chunk * p.zc;
-    const int z1 = min(z0 + p.zc, p.zbase + p.zcount);
-    const int n2 = p.n2, n3 = p.n3;
-    const int64_t s3 = p.s3;
-    const int bsel = batch / p.nhyp, bhyp = batch - bsel * p.nhyp;
-    const int64_t boff = (int64_t)bhyp * p.s4;
-
-    const bool closed = (p.nchunks == 1 && p.zcount == p.n3);
-    const int nsteps = closed ? (z1 - z0) : (z1 - z0) + L - 1;
-    const uint32_t stage_bytes = (uint32_t)(stage_elems * sizeof(T));
-
-    const int r0 = wrapi(a2 - HB, n2);
-    const int rows0 = min(W2, n2 - r0);
-    int iz = wrapi(z0 - HB, n3);                                  // plane of the next stage to issue
-    int iq = 0;                                                   // group (= stage) of the next stage to issue
-    auto issue = [&]() {   // stages are issued in order: group iq of plane iz into stage iq
-        if (tid == 0) {
-            mbar_expect_tx(bar + iq, stage_bytes);
-            const int blo = 8 * bsel + (iq & 1) + 4 * (iq >> 1);
-            T *dst = STG + (size_t)iq * stage_elems;
-#pragma unroll
-            for (int hb = 0; hb < 2; ++hb) {
-                const T *src = p.in[blo + 2 * hb] + boff + (int64_t)iz * s3;
-                T *d = dst + hb * W2 * n1;
-                bulk_g2s(d, src + (int64_t)r0 * n1, (uint32_t)(rows0 * n1 * sizeof(T)), bar + iq);
-                if (rows0 < W2) bulk_g2s(d + rows0 * n1, src, (uint32_t)((W2 - rows0) * n1 * sizeof(T)), bar + iq);
-            }
-        }
-        if (++iq == 4) { iq = 0; if (++iz == n3) iz = 0; }
-    };
-
-    const int CPR = n1 / VEC, NC_ITEMS = T2 * CPR;
-    int c_src[KC];
-    T *c_out[KC];
-    bool c_ok[KC];
-    T acc[KC][L][VEC];
-#pragma unroll
-    for (int k = 0; k < KC; ++k) {
-        const int it = tid + k * NT;
-        const int j = (it / CPR) % T2, cp = it - (it / CPR) * CPR;
-        c_src[k] = j * pv + cp * VEC;
-        c_ok[k] = (it < NC_ITEMS) && (a2 + j < n2);
-        c_out[k] = p.out[bsel] + boff + ((int64_t)z0 - (L - 1)) * s3 + (int64_t)(a2 + j) * n1 + cp * VEC;
-#pragma unroll
-        for (int s = 0; s < L; ++s)
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) acc[k][s][e] = zero_of(T());
-    }
-
-    if (tid == 0) {
-        for (int i = 0; i < NSTG; ++i) mbar_init(bar + i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (nsteps > 0)
-        for (int i = 0; i < 4; ++i) issue();
-
-    // stage RA: thread = (group gsel of the pair, column c), full tile height
-    const int gsel = (tid >= n1) ? 1 : 0;
-    const int ca = tid - gsel * n1;
-    const bool ra_on = tid < 2 * n1;
-    const int wl = (ca >= n1 - HB) ? -n1 : 0;      // left-pad copy of columns n1-HB .. n1-1
-    const int wr = (ca < HA) ? n1 : 0;             // right-pad copy of columns 0 .. HA-1
-    const int NB_ITEMS = T2 * (n1 / R1B);
-    int u = 0;
-    for (int t = 0; t < nsteps; ++t) {
-        const uint32_t parity = (uint32_t)(t & 1);
-        const bool store = closed || (t >= L - 1);
-        const int64_t wrap_off = (closed && t < L - 1) ? (int64_t)n3 * s3 : 0;   // early partials of the wrapped planes
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {       // m = b3
-            // ---- stage RA: dim 2 for groups (2m, 2m+1), one column over the full height per thread
-            if (ra_on) {
-                const int q = 2 * m + gsel;
-                mbar_wait(bar + q, parity);
-                const T *s0 = STG + (size_t)q * stage_elems + ca;
-                const T *s1 = s0 + W2 * n1;
-                T w0[W2], w1[W2];
-#pragma unroll
-                for (int i = 0; i < W2; ++i) {
-                    w0[i] = s0[i * n1];
-                    w1[i] = s1[i * n1];
-                }
-                T o0[T2], o1[T2];
-#pragma unroll
-                for (int i = 0; i < T2; ++i) { o0[i] = zero_of(T()); o1[i] = zero_of(T()); }
-#pragma unroll
-                for (int kk = 0; kk < L; ++kk)
-#pragma unroll
-                    for (int i = 0; i < T2; ++i) {
-                        macp(o0[i], tp.lo[1][kk], w0[i + kk]);
-                        macp(o1[i], tp.hi[1][kk], w1[i + kk]);
-                    }
-                T *dst = SU + gsel * T2 * pu + HB + ca;
-#pragma unroll
-                for (int i = 0; i < T2; ++i) {
-                    o0[i] = add(o0[i], o1[i]);
-                    dst[i * pu] = o0[i];
-                }
-                if (wl | wr) {
-                    const int wo = wl ? wl : wr;
-#pragma unroll
-                    for (int i = 0; i < T2; ++i) dst[i * pu + wo] = o0[i];
-                }
-            }
-            __syncthreads();   // both stages consumed, SU complete (and SV free: its readers passed this barrier)
-            if (t + 1 < nsteps) { issue(); issue(); }
-
-            // ---- stage RB: dim 1 for b3 = m
-            for (int it = tid; it < NB_ITEMS; it += NT) {
-                const int j = it % T2, cb = it / T2;
-                const T *ra = SU + j * pu + cb * R1B;
-                const T *rb = ra + T2 * pu;
-                T va[NCHB * VEC], vb[NCHB * VEC];
-#pragma unroll
-                for (int c = 0; c < NCHB; ++c) {
-                    ld_chunk<T, VEC>(ra + c * VEC, va + c * VEC);
-                    ld_chunk<T, VEC>(rb + c * VEC, vb + c * VEC);
-                }
-                T o[R1B], ob[R1B];
-#pragma unroll
-                for (int i = 0; i < R1B; ++i) { o[i] = zero_of(T()); ob[i] = zero_of(T()); }
-#pragma unroll
-                for (int kk = 0; kk < L; ++kk)
-#pragma unroll
-                    for (int i = 0; i < R1B; ++i) {
-                        macp(o[i], tp.lo[0][kk], va[i + kk]);
-                        macp(ob[i], tp.hi[0][kk], vb[i + kk]);
-                    }
-#pragma unroll
-                for (int i = 0; i < R1B; ++i) o[i] = add(o[i], ob[i]);
-                T *d = SV + j * pv + cb * R1B;
-#pragma unroll
-                for (int c = 0; c < R1B / VEC; ++c) st_chunk<T, VEC>(d + c * VEC, o + c * VEC);
-            }
-            __syncthreads();   // SV complete (and SU free for the next pair)
-
-            // ---- stage RC, half m: dim-3 scatter ring with the lo3 (m = 0) / hi3 (m = 1) taps; the plane that is
-            // complete leaves after the second half
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                if (tid + k * NT < NC_ITEMS) {
-                    T v[VEC];
-                    ld_chunk<T, VEC>(SV + c_src[k], v);
-                    if (m == 0) DispatchCH<T, L, VEC, 0, 0>::run(u, acc[k], v, tp.lo[2], nullptr, false);
-                    else {
-                        DispatchCH<T, L, VEC, 0, 1>::run(u, acc[k], v, tp.hi[2], c_out[k] + wrap_off, store && c_ok[k]);
-                        c_out[k] += s3;
-                    }
-                }
-            }
-        }
-        u = (u + 1 == L) ? 0 : u + 1;
-    }
-    if (closed) {   // flush: planes n3-L+1 .. n3-1 = early partial (already in memory) + what is left in the ring
-        for (int f = 0; f < L - 1; ++f) {
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                if (tid + k * NT < NC_ITEMS) {
-                    T v0[VEC], v1[VEC];
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) { v0[e] = zero_of(T()); v1[e] = zero_of(T()); }
-                    DispatchC<T, L, VEC, 0>::run(u, acc[k], v0, v1, tp.lo[2], tp.hi[2], c_out[k], c_ok[k], true);
-                    c_out[k] += s3;
-                }
-            }
-            u = (u + 1 == L) ? 0 : u + 1;
-        }
-    }
-}
-
-
-// ---------------------------------------------------------------------------------------------
 // Last-dimension passes of the 4-D path (and the slab-exchange points of the multi-GPU path):
 // one thread owns one 16-byte chunk of the (dim 1..3) hyperplane and marches along dim 4 with an
 // L-deep register ring, so every input hyperplane is read exactly once.
@@ -1799,7 +1556,8 @@ static int launch_dec3_any(nddwt_plan *p, const Dec3Params<T> &prm, cudaStream_t
     // incremental plane pointer (ZINC): no integer modulo per plane in stage A; SHR: soft threshold fused into the stores
     // shrink epilogue: one-row stage-C runs keep it spill-free (two-row runs: 260 B of spills, 6.8 vs 4.4 ms on cfg5)
     if (p->shrink_mode) return launch_dec3_v<T, L, 16, 256, 1, 2, 0, 1, 1, 1>(p, prm, s);
-    if (p->shrink_variant == 2) return launch_dec3_v<T, L, 16, 256, 1, 2, 0, 1, 1>(p, prm, s);
+    // (stage B shared evenly by all warps -- every thread half an item in the last half-iteration -- measured
+    // slower: 3.9-4.1 vs 3.65-3.7 ms, profiles/r02_variants.md)
     return launch_dec3_v<T, L, 16, 256, 2, 2, 0, 1, 1>(p, prm, s);
 }
 
@@ -2029,57 +1787,14 @@ static int launch_rec3_rows_n(nddwt_plan *p, const Rec3Params<T> &base, cudaStre
     return 0;
 }
 
-// paired full-row synthesis kernel: returns -1 when the geometry does not fit (caller falls back)
-template <typename T, int L, int T2, int NT, int KC, int N1>
-static int launch_rec3_rows2_n(nddwt_plan *p, const Rec3Params<T> &base, cudaStream_t s)
-{
-    constexpr int VEC = 16 / (int)sizeof(T), W2 = T2 + L - 1;
-    Rec3Params<T> prm = base;
-    const int n1 = prm.n1;
-    if (sizeof(T) != 8 || (N1 && n1 != N1) || n1 % (2 * VEC) != 0 || n1 < 4 * VEC || 2 * n1 > NT ||
-        T2 * (n1 / VEC) > KC * NT || prm.n2 < W2)
-        return -1;
-    RowsGeo g;
-    g.pu = rows_pu<T, L>(n1);
-    g.pv = rows_pv<T>(n1);
-    g.stage_elems = 2 * W2 * n1;
-    g.nstg = 4;
-    const size_t smem = ((size_t)4 * g.stage_elems + (size_t)2 * T2 * g.pu + (size_t)T2 * g.pv) * sizeof(T) + 64;
-    if (smem > 227 * 1024) return -1;
-    prm.tiles1 = 1;
-    prm.tiles2 = (prm.n2 + T2 - 1) / T2;
-    const int batches = prm.nhyp * (prm.out[1] ? 2 : 1);
-    if (prm.zcount <= 0) { prm.zbase = 0; prm.zcount = prm.n3; }
-    prm.zc = pick_zc_rec(prm.zcount, prm.tiles2 * batches, L - 1, 148, prm.zcount == prm.n3);
-    prm.nchunks = (prm.zcount + prm.zc - 1) / prm.zc;
-    if ((int64_t)prm.tiles2 * batches * prm.nchunks < p->rows_min_ctas) return -1;
-    prm.prefetch = 0;
-    prm.cl1 = prm.cl2 = 1;
-    prm.hint = 0;
-    p->last_rec_kernel = 4;
-    auto kern = k_rec3_rows2<T, L, T2, NT, KC, N1>;
-    NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per-device attribute: set on every launch
-    const FusedTaps<T, L> tp = make_taps<T, L>(p, true);
-    const int64_t grid = (int64_t)prm.tiles2 * prm.nchunks * batches;
-    {
-        LaunchTimer lt(p, KIND_REC3, s);
-        kern<<<(unsigned)grid, NT, smem, s>>>(prm, tp, g);
-    }
-    p->launches++;
-    NDDWT_CUDA(cudaGetLastError());
-    return 0;
-}
-
 template <typename T, int L>
 static int launch_rec3_rows(nddwt_plan *p, const Rec3Params<T> &prm, cudaStream_t s)
 {
     // RASPLIT = 1 / RBM = 2 (19 % fewer shared-memory wavefronts, but half of the warps idle in those stages)
     // measured slower in round 2: 3.87 / 3.70 / 3.93 ms vs 3.64 ms (profiles/r02_variants.md)
-    if (p->rows_variant == 2) {      // paired form (rows of at most 192 elements)
-        const int rc = prm.n1 == 192 ? launch_rec3_rows2_n<T, L, 8, 384, 2, 192>(p, prm, s)
-                                     : launch_rec3_rows2_n<T, L, 8, 384, 2, 0>(p, prm, s);
-        if (rc >= 0) return rc;
-    }
+    // A paired-group form (both b1 groups of a b3 at once, full-height stage RA that reads every staged element
+    // once, 4-stage ring, stage RC in halves: -32 % stage-RA wavefronts, 4 barriers per plane instead of 5) was
+    // correct on every test shape and slower: 3.86 vs 3.75 ms on cfg5 (profiles/r02_variants.md); removed.
     if (prm.n1 == 192) return launch_rec3_rows_n<T, L, 8, 384, 2, 192>(p, prm, s);
     if (prm.n1 == 256) return launch_rec3_rows_n<T, L, 8, 512, 2, 256>(p, prm, s);   // 2-stage ring (224 KB), 128-register cap
     return launch_rec3_rows_n<T, L, 8, 384, 2, 0>(p, prm, s);

@@ -34,8 +34,6 @@ struct nddwt_plan {
     // analysis kernels store them; thr[j-1][b] for level j, band b (b = 0, the approximation, is exempt)
     int shrink_mode = 0;
     double shrink_thr[NDDWT_MAX_LEVELS][1 << NDDWT_MAX_DIMS];
-    int shrink_variant = 0;
-    int rows_variant = 0;      // full-row synthesis kernel: 0 = one group per step, 2 = paired groups (nddwt_plan_set_param)
     int cur_level = 1;         // level index of the level call in flight (selects the threshold row)
     int rows_min_ctas = 118;   // full-row synthesis kernel needs at least this many CTAs (nddwt_plan_set_param)
 

@@ -359,8 +359,7 @@ def test_fused_1d_cascade(n, wn, level, dtype):
                                       ("db2", "float64"), ("db4", "float64")])
 @pytest.mark.parametrize("sizes,level", [((64, 30, 9, 8), 1), ((192, 40, 16, 8), 1), ((72, 20, 8, 8), 1),
                                           ((128, 17, 12), 1), ((32, 32, 24, 16), 2), ((64, 32, 12, 16), 2), ((256, 20, 8, 8), 1)])
-@pytest.mark.parametrize("rows_variant", [0, 2], ids=["single", "paired"])
-def test_full_row_synthesis_kernel(sizes, level, wn, dtype, rows_variant):
+def test_full_row_synthesis_kernel(sizes, level, wn, dtype):
     """k_rec3_rows (full-row tiles, 8-byte elements) is chosen by default only for big 4-D batches; lower
     its CTA bound so that small, odd shapes (dim-2 wrap inside a tile, partial last tile, dim-3/4 shorter
     than two rings) reach it, and compare with the generic kernels and the oracle."""
@@ -371,8 +370,6 @@ def test_full_row_synthesis_kernel(sizes, level, wn, dtype, rows_variant):
     g = _obj(sizes, wn, 0, prec, kernel_mode=1)
     a.set_param("rows_min_ctas", 0)
     b.set_param("rows_min_ctas", 0)
-    a.set_param("rows_variant", rows_variant)      # 2: paired-group form (rows of at most 192 elements), else it falls back
-    b.set_param("rows_variant", rows_variant)
     y = a.dec(x, level)
     assert orc.rel_l2(a.rec(y), x) <= TOL[prec]
     assert a.synthesis_kernels() == [4], a.synthesis_kernels()
