@@ -142,7 +142,7 @@ def cpu_reference_pair(sizes, wname, level, dtype, threads, budget_s=25.0, batch
         ref_mex.rec(y, wname, False)
         results["ref_mex_c128"] = nvox / (time.perf_counter() - t0) / 1e6
     best_kind = max(results, key=results.get)
-    return {"value": results[best_kind], "unit": "Mvoxels/s", "cores": threads, "sample_voxels": nvox,
+    return {"value": results[best_kind], "unit": "Mvoxels/s", "cores": threads, "sample_voxels": nvox, "sample_sizes": list(samp),
             "kind": "reference" if best_kind == "ref_mex_c128" else "port",
             "sample": "%s %s J%d %s, one dec+rec pair; port('mat' path, scipy.fft workers=%d)=%.3f Mvox/s%s; PR err %.1e"
                       % ("x".join(map(str, samp)), wname, level, dtype, threads, results["port_mat"],
@@ -173,7 +173,11 @@ def run_reference(args, wl_name, wl):
             "ms_per_step": base["sample_voxels"] / (v * 1e6) * 1e3,   # one dec+rec pair of the bounded sample
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c64",
             "data": "synthetic", "config": {"workload": wl_name, "sizes": list(sizes), "wavelet": wname,
-                                            "levels": level, "elem": dtype},
+                                            "levels": level, "elem": dtype,
+                                            "sampled_sizes": base.get("sample_sizes"),
+                                            "sample_note": "the CPU path is timed on a bounded sample of the workload "
+                                                           "(same dims, wavelet, levels; per-voxel rate reported): at full "
+                                                           "size its stored filters alone need 2^d x the array"},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "Mvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

@@ -357,7 +357,7 @@ def run_multi(args, wl_name, wl):
                        "transport": ("peer memory: copy-engine pushes over NVLink into CUDA-IPC inboxes, flags in peer "
                                      "memory (nddwt_mplan_*)") if transport == "peer" else
                                     "NCCL send/recv per level (torch.distributed batch_isend_irecv)",
-                       "transport_fallback": fallback, "flag_wait_timeouts": timeouts, "comm_streams": COMM_STREAMS or "default (1)", "z_chunks": Z_CHUNKS or "default (4)",
+                       "transport_fallback": fallback, "flag_wait_timeouts": timeouts, "comm_streams": COMM_STREAMS or "default (1)", "z_chunks": Z_CHUNKS or "automatic (4 when the halo exceeds the slab, 2 down to a third of it, else 1)",
                        "l2": "per-GPU working set %.1f GB >> L2, no flush" % ((1 + nb) * nvox * esize / world / 1e9),
                        "pr_rel_err": pr_err, "dec_rel_err": e_dec, "parity_rec_rel_err": e_rec,
                        "parity_case": {"sizes": small, "what": "rank 0's slab of dec vs the oracle, reconstruction on every rank"},

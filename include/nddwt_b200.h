@@ -222,8 +222,10 @@ NDDWT_API int nddwt_mplan_is_separable(const nddwt_mplan *mplan); /* 1: overlapp
 NDDWT_API int nddwt_mplan_set_dilations(nddwt_mplan *mplan, const int *dil, int nlevels);  /* a-trous: halos (L-1)*dil */
 NDDWT_API int nddwt_mplan_set_kernel_mode(nddwt_mplan *mplan, int mode);
 NDDWT_API int nddwt_mplan_set_shrink(nddwt_mplan *mplan, int mode, const double *thr, int nlevels);   /* nddwt_plan_set_shrink on every rank */
-/* "comm_streams" (1..4, default 2): every pushed run of planes is cut in that many pieces which travel on
- * different streams / copy engines at once; other names are forwarded to the per-rank plans. */
+/* "z_chunks" (0..64, default 0 = chosen from the halo : slab ratio): fused 4-D plans issue a level in that many
+ * chunks of dim 3, so that the halo planes of one chunk travel while the next chunk computes; "comm_streams" (1..4,
+ * default 1): every pushed run of planes is cut in that many pieces which travel on different streams / copy
+ * engines at once; other names are forwarded to the per-rank plans. */
 NDDWT_API int nddwt_mplan_set_param(nddwt_mplan *mplan, const char *name, int64_t value);
 
 /* y = dec(x, level) / x = rec(y) on slabs.  x_slabs / coeff_slabs: one DEVICE pointer per local rank (in

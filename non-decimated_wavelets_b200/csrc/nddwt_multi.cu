@@ -88,8 +88,9 @@ struct nddwt_mplan {
     int64_t extra_launches = 0;
     int64_t copies = 0, copy_bytes = 0;
     int comm_streams = 1;                    // copy streams per rank (1..4), nddwt_mplan_set_param("comm_streams")
-    int z_chunks = 4;                        // separable 4-D plans: a level is issued in this many dim-3 chunks so that
+    int z_chunks = 0;                        // separable 4-D plans: a level is issued in this many dim-3 chunks so that
                                              // the halo planes of one chunk travel while the next chunk computes
+                                             // (0 = chosen from the halo : slab ratio, see make_chunks)
 };
 
 namespace nddwt {
@@ -494,6 +495,15 @@ static Chunks make_chunks(const nddwt_mplan *mp)
     Chunks ch;
     const int n3 = (int)mp->dims[2];
     int C = mp->z_chunks;
+    if (C <= 0) {
+        // Chunking hides the flight of the halo planes behind compute but costs extra kernel tails and ring warm-ups;
+        // it pays when the halo is large against the slab (measured on cfg4, profiles/r02_multi_gpu.md: 4 planes per
+        // rank 23.2 -> 19.5 ms with 4 chunks; 16 planes per rank 66.2 / 65.7 / 67.3 ms with 1 / 2 / 4 chunks)
+        int64_t maxc = 1;
+        for (int64_t c : mp->count) maxc = c > maxc ? c : maxc;
+        const double ratio = (double)(mp->L_last - 1) / (double)maxc;
+        C = ratio > 1.2 ? 4 : (ratio > 0.3 ? 2 : 1);
+    }
     if (C > n3 / 8) C = n3 / 8;      // a chunk must be wider than the dim-3 filter support
     if (C < 1) C = 1;
     ch.C = C;
@@ -978,7 +988,7 @@ int nddwt_mplan_set_param(nddwt_mplan *mp, const char *name, int64_t value)
 {
     if (!mp || !name) { set_error("null argument"); return NDDWT_ERR_ARG; }
     if (strcmp(name, "z_chunks") == 0) {
-        if (value < 1 || value > 64) { set_error("z_chunks must be 1..64"); return NDDWT_ERR_ARG; }
+        if (value < 0 || value > 64) { set_error("z_chunks must be 0 (automatic) .. 64"); return NDDWT_ERR_ARG; }
         mp->z_chunks = (int)value;
         return 0;
     }
