@@ -375,7 +375,8 @@ def main():
     # DRAM traffic of the dominant kernel per launch, from the committed ncu capture of this command
     traffic = None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_launch_summary_%s.json" % wl_name)))
+        cand = [os.path.join(ROOT, "profiles", "r%02d_launch_summary_%s.json" % (r, wl_name)) for r in (2, 1)]
+        prof = json.load(open([c for c in cand if os.path.exists(c)][0]))
         key = {0: "k_dec3", 1: "k_rec3", 2: "k_dec_last", 3: "k_rec_last"}.get(dom, "?")
         for name, rec in prof["kernels"].items():
             if key in name:
