@@ -96,3 +96,37 @@ def test_rec_rejects_bad_band_count():
         o.rec(np.zeros((8, 8, 5)))
     with pytest.raises(ValueError, match="not consistant"):
         o.dec(np.zeros((8, 9)), 1)
+
+
+def test_shrink_threshold_tables_host_side():
+    """set_shrink accepts a scalar, one value per level, or a [J][2^d] table; negative values are refused.  (The
+    table reaches the device plans at the next dec; no GPU is needed to build it.)"""
+    o = nd.nd_dwt_3D("db2", [16, 16, 16], "precision", "single")
+    o.set_shrink(0.5)
+    assert o.shrink.shape == (16, 8) and np.all(o.shrink == 0.5)
+    o.set_shrink([0.1, 0.2, 0.3])
+    assert o.shrink.shape == (3, 8) and np.allclose(o.shrink[:, 5], [0.1, 0.2, 0.3])
+    t = np.arange(16, dtype=float).reshape(2, 8)
+    o.set_shrink(t)
+    assert np.array_equal(o.shrink, t)
+    o.set_shrink(None)
+    assert o.shrink is None
+    with pytest.raises(ValueError):
+        o.set_shrink(-0.1)
+    with pytest.raises(ValueError):
+        o.set_shrink(np.zeros((2, 4)))      # a 3-D transform has 8 bands per level
+
+
+def test_multi_gpu_options_and_export_blob_size():
+    L = nd.lib()
+    assert L.nddwt_mplan_export_size() >= 64 + 16          # a CUDA IPC handle + geometry
+    o = nd.nd_dwt_4D("db4", [32, 24, 16, 12], "ngpus", 4)
+    assert o.ngpus == 4 and o.devices is None
+    o = nd.nd_dwt_4D("db4", [32, 24, 16, 12], "devices", [0, 0, 0])
+    assert o.ngpus == 3 and o.devices == [0, 0, 0]
+    # soft threshold of the oracle: identity at t = 0, approximation band exempt
+    x = orc.synth((12, 10), np.complex128, 2)
+    y = orc.dec_direct(x, "db2", 2)
+    assert np.array_equal(orc.shrink_soft(y, np.zeros((2, 4)), 2), y)
+    ys = orc.shrink_soft(y, np.full((2, 4), 1e9), 2)
+    assert np.array_equal(ys[..., 0], y[..., 0]) and not ys[..., 1:].any()
