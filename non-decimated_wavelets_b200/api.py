@@ -115,6 +115,7 @@ class _NdDwtBase:
         self.method = "fft"
         self.ngpus = 1
         self.devices = None
+        self.dilations = None
         opts = list(zip(varargin[0::2], varargin[1::2])) + list(kwargs.items())
         for ind, (key, val) in enumerate(opts):
             k = str(key).lower()
@@ -124,6 +125,9 @@ class _NdDwtBase:
                 self.compute = str(val)
             elif k == "precision":
                 self.precision = str(val)
+            elif k == "atrous":        # extension: true a-trous transform, dilation 2^(j-1) at level j (the reference
+                if val:                #            re-applies undilated filters, nd_dwt_2D.m:183)
+                    self.dilations = [1 << j for j in range(_lib_max_levels())]
             elif k == "ngpus":         # extension: slabs of the last dimension over several GPUs (host arrays)
                 self.ngpus = int(val)
             elif k == "devices":       # extension: explicit device list for 'ngpus' (repeat an index to emulate ranks)
@@ -143,7 +147,6 @@ class _NdDwtBase:
             if len(lo) > self.sizes[i]:
                 raise ValueError("Dimension %d of Data is shorter than the wavelet filter being used" % (i + 1))
         self._plans = {}
-        self.dilations = None
         self.kernel_mode = 0
         self.params = {}
         self.shrink = None
@@ -198,8 +201,8 @@ class _NdDwtBase:
         if pl is None:
             devs = self.devices if self.devices is not None else list(range(self.ngpus))
             pl = _lib.MultiPlan(self.sizes, self.wname, code, self.pres_l2_norm, devices=devs)
-            if self.dilations is not None:
-                pl.set_dilations(self.dilations)
+            if self.dilations is not None:      # halo buffers are sized by the largest dilation: keep the useful levels
+                pl.set_dilations([d for d in self.dilations if d <= self.sizes[-1]] or [1])
             pl.set_kernel_mode(self.kernel_mode)
             for name, value in self.params.items():
                 pl.set_param(name, value)

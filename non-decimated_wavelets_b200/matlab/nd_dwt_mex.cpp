@@ -18,6 +18,7 @@
 //     h = nd_dwt_mex('plan', f, is_single, is_complex, pres_l2_norm [, ngpus])   uint64 handle; ngpus > 1: the
 //                                                                            multi-GPU plan (host arrays only)
 //     nd_dwt_mex('shrink', h, table)      soft-threshold table [J x 2^d] fused into later dec calls ([] = off)
+//     nd_dwt_mex('dilations', h, dil)     a-trous mode: dilation of the taps per level (default 1 everywhere = reference)
 //     nd_dwt_mex('release', h) / nd_dwt_mex('release')
 // Build:  mex -R2018a nd_dwt_mex.cpp -I../../include -L.. -lnddwt_b200                  (host arrays)
 //         mexcuda -R2018a -DNDDWT_MEX_GPU nd_dwt_mex.cpp -I../../include -L.. -lnddwt_b200   (+ gpuArray)
@@ -212,6 +213,18 @@ extern "C" void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *
                     for (int b = 0; b < nd; ++b) tab[j * nd + b] = src[(size_t)b * J + j];
                 rc = e->plan ? nddwt_plan_set_shrink(e->plan, 1, tab, J) : nddwt_mplan_set_shrink(e->mplan, 1, tab, J);
             }
+            if (rc) fail_lib();
+            return;
+        }
+        if (strcmp(cmd, "dilations") == 0 && nrhs == 3) {       // nd_dwt_mex('dilations', h, dil)   a-trous: dilation per level
+            Entry *e = entry_of_handle(prhs[1]);
+            if (!e) fail("not a plan handle");
+            const int n = (int)mxGetNumberOfElements(prhs[2]);
+            if (!mxIsDouble(prhs[2]) || n < 1 || n > NDDWT_MAX_LEVELS) fail("dilations: 1..16 positive values");
+            int dil[NDDWT_MAX_LEVELS];
+            const double *src = mxGetDoubles(prhs[2]);
+            for (int j = 0; j < n; ++j) dil[j] = (int)src[j];
+            const int rc = e->plan ? nddwt_plan_set_dilations(e->plan, dil, n) : nddwt_mplan_set_dilations(e->mplan, dil, n);
             if (rc) fail_lib();
             return;
         }

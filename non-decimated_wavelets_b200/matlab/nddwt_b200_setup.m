@@ -28,6 +28,7 @@ obj.pres_l2_norm = 0;
 obj.precision = 'double';
 obj.compute = 'mat';
 ngpus = 1;
+atrous = false;
 for k = 1:2:numel(opts)
     key = lower(opts{k});
     val = opts{k + 1};
@@ -37,6 +38,8 @@ for k = 1:2:numel(opts)
         obj.compute = val;
     elseif strcmp(key, 'precision')
         obj.precision = val;
+    elseif strcmp(key, 'atrous')         % extension: true a-trous transform, dilation 2^(j-1) at level j
+        atrous = logical(val);
     elseif strcmp(key, 'ngpus')          % extension: slabs along the last dimension over several GPUs (host arrays)
         ngpus = double(val);
     elseif any(strcmp(key, extra_keys))
@@ -64,4 +67,11 @@ is_single = strcmpi(obj.precision, 'single');
 obj.plan_h = [nd_dwt_mex('plan', obj.f_dec, is_single, false, obj.pres_l2_norm, ngpus), ...
               nd_dwt_mex('plan', obj.f_dec, is_single, true, obj.pres_l2_norm, ngpus)];
 obj.ngpus = ngpus;
+if atrous
+    dil = 2 .^ (0:15);
+    dil = dil(dil <= obj.sizes(end));
+    for h = obj.plan_h
+        nd_dwt_mex('dilations', h, dil);
+    end
+end
 end

@@ -290,6 +290,23 @@ def test_dilated_atrous_mode_opt_in():
     assert orc.rel_l2(o.rec(y), x) <= 1e-12
 
 
+def test_atrous_option_and_haar_multilevel():
+    """'atrous' option (extension): dilation 2^(j-1) at level j -- the transform the literature calls
+    non-decimated -- for the Daubechies classes and as the multi-level Haar that harr_nddwt_4D.m:175,222 does not
+    compute correctly.  Oracle: the closed-form restatement with the same dilations; perfect reconstruction."""
+    x = orc.synth((24, 20, 16, 16), np.complex64, 6)
+    h = nd.harr_nddwt_4D([24, 20, 16, 16], "precision", "single", "atrous", 1)
+    y = h.dec(x, 3)
+    assert orc.rel_l2(y, orc.dec_direct(x.astype(np.complex128), "db1", 3, dilations=[1, 2, 4])) <= 1e-5
+    assert orc.rel_l2(h.rec(y), x) <= 1e-5
+    x3 = orc.synth((40, 36, 32), np.complex128, 7)
+    o = nd.nd_dwt_3D("db3", [40, 36, 32], "pres_l2_norm", 1, "atrous", True)
+    y3 = o.dec(x3, 2)
+    assert orc.rel_l2(y3, orc.dec_direct(x3, "db3", 2, True, dilations=[1, 2])) <= 1e-12
+    assert orc.rel_l2(o.rec(y3), x3) <= 1e-12
+    assert abs(np.linalg.norm(y3.ravel()) / np.linalg.norm(x3.ravel()) - 1) < 1e-11      # still a tight frame
+
+
 def test_4d_full_size_properties_cfg5():
     """Size-independent properties at BASELINE configs[4]'s full size (192x192x64x48 complex single,
     db4, 3 levels; the bench.py N=1 workload): perfect reconstruction, linearity, energy."""
