@@ -447,8 +447,9 @@ struct GeoR {
 template <typename T, int L, int VEC, int U>
 __device__ __forceinline__ void rec_stage_c(T (&acc)[L][VEC], const T (&v0)[VEC], const T (&v1)[VEC],
                                             const typename TapOf<T>::type *lo, const typename TapOf<T>::type *hi,
-                                            T *dst, bool store, bool rmw = false)
+                                            T *dst, bool store, bool rmw = false, int nel = -1)
 {
+    // nel >= 0: rows that are not 16-byte multiples -- the completed chunk leaves element by element, nel of them
     // coefficient plane t (phase U = t mod L) feeds output planes n = z0 + t - k, slot (U - k) mod L
 #pragma unroll
     for (int k = 0; k < L; ++k) {
@@ -459,7 +460,11 @@ __device__ __forceinline__ void rec_stage_c(T (&acc)[L][VEC], const T (&v0)[VEC]
         }
     }
     // plane n = z0 + t - (L-1) is complete: slot (U + 1) mod L
-    if (store) {
+    if (store && nel >= 0) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+            if (e < nel) st_stream(dst + e, acc[(U + 1) % L][e]);
+    } else if (store) {
         union { uint4 q; T t[VEC]; } a;
 #pragma unroll
         for (int e = 0; e < VEC; ++e) a.t[e] = acc[(U + 1) % L][e];
@@ -479,20 +484,20 @@ template <typename T, int L, int VEC, int U>
 struct DispatchC {
     __device__ __forceinline__ static void run(int u, T (&acc)[L][VEC], const T (&v0)[VEC], const T (&v1)[VEC],
                                                const typename TapOf<T>::type *lo, const typename TapOf<T>::type *hi,
-                                               T *dst, bool store, bool rmw = false)
+                                               T *dst, bool store, bool rmw = false, int nel = -1)
     {
-        if (u == U) rec_stage_c<T, L, VEC, U>(acc, v0, v1, lo, hi, dst, store, rmw);
-        else DispatchC<T, L, VEC, U + 1>::run(u, acc, v0, v1, lo, hi, dst, store, rmw);
+        if (u == U) rec_stage_c<T, L, VEC, U>(acc, v0, v1, lo, hi, dst, store, rmw, nel);
+        else DispatchC<T, L, VEC, U + 1>::run(u, acc, v0, v1, lo, hi, dst, store, rmw, nel);
     }
 };
 template <typename T, int L, int VEC>
 struct DispatchC<T, L, VEC, L> {
     __device__ __forceinline__ static void run(int, T (&)[L][VEC], const T (&)[VEC], const T (&)[VEC],
                                                const typename TapOf<T>::type *, const typename TapOf<T>::type *, T *,
-                                               bool, bool = false) {}
+                                               bool, bool = false, int = -1) {}
 };
 
-template <typename T, int L, int T2, int NT, int R2, int MINB>
+template <typename T, int L, int T2, int NT, int R2, int MINB, int EDGE = 0>
 __global__ void __launch_bounds__(NT, MINB)
 k_rec3_fused(const Rec3Params<T> p, const FusedTaps<T, L> tp)
 {
@@ -560,6 +565,7 @@ k_rec3_fused(const Rec3Params<T> p, const FusedTaps<T, L> tp)
     int c_src[KC];
     T *c_out[KC];
     bool c_ok[KC];
+    int c_nel[EDGE ? KC : 1];
     T acc[KC][L][VEC];
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
@@ -568,6 +574,7 @@ k_rec3_fused(const Rec3Params<T> p, const FusedTaps<T, L> tp)
         c_src[k] = j * PV + cp * VEC;
         const int g1 = a1 + cp * VEC, g2 = a2 + j;
         c_ok[k] = (it < NC_ITEMS) && g1 < n1 && g2 < n2;
+        if (EDGE) c_nel[k] = min(VEC, n1 - g1);     // rows that are not 16-byte multiples: element-wise, guarded stores
         // pointer to output plane (z0 - (L-1)): advanced by s3 per step, first stored at step t = L-1
         c_out[k] = p.out[bsel] + boff + ((int64_t)z0 - (L - 1)) * s3 + (int64_t)g2 * n1 + g1;
 #pragma unroll
@@ -671,7 +678,8 @@ k_rec3_fused(const Rec3Params<T> p, const FusedTaps<T, L> tp)
                 T v0[VEC], v1[VEC];
                 ld_chunk<T, VEC>(SV + c_src[k], v0);
                 ld_chunk<T, VEC>(SV + c_src[k] + T2 * PV, v1);
-                DispatchC<T, L, VEC, 0>::run(u, acc[k], v0, v1, tp.lo[2], tp.hi[2], c_out[k], store && c_ok[k]);
+                DispatchC<T, L, VEC, 0>::run(u, acc[k], v0, v1, tp.lo[2], tp.hi[2], c_out[k], store && c_ok[k], false,
+                                             EDGE ? c_nel[k] : -1);
                 c_out[k] += s3;
             }
         }
@@ -1553,6 +1561,9 @@ static int launch_dec3_any(nddwt_plan *p, const Dec3Params<T> &prm, cudaStream_t
         }
     }
 #endif
+    // rows that are not 16-byte multiples: element-wise stage-C columns and stores (plans with the fused shrink never get
+    // here with such rows: dec_rows_ok)
+    if (prm.n1 % (16 / (int)sizeof(T)) != 0) return launch_dec3_v<T, L, 16, 256, 8, 2, 1, 1, 1>(p, prm, s);
     // incremental plane pointer (ZINC): no integer modulo per plane in stage A; SHR: soft threshold fused into the stores
     // shrink epilogue: one-row stage-C runs keep it spill-free (two-row runs: 260 B of spills, 6.8 vs 4.4 ms on cfg5)
     if (p->shrink_mode) return launch_dec3_v<T, L, 16, 256, 1, 2, 0, 1, 1, 1>(p, prm, s);
@@ -1610,7 +1621,7 @@ static int pick_zc_rec(int n3, int units_per_plane_chunk, int H, int slots, bool
     return best;
 }
 
-template <typename T, int L, int T2, int NT, int R2, int MINB>
+template <typename T, int L, int T2, int NT, int R2, int MINB, int EDGE = 0>
 static int launch_rec3_v(nddwt_plan *p, const Rec3Params<T> &base, cudaStream_t s)
 {
     using G = GeoR<T, L, T2>;
@@ -1623,7 +1634,7 @@ static int launch_rec3_v(nddwt_plan *p, const Rec3Params<T> &base, cudaStream_t 
     prm.nchunks = (prm.zcount + prm.zc - 1) / prm.zc;
     prm.prefetch = tuning_env("NDDWT_PREFETCH", 0);   // prefetch.global.L1/L2 of the next plane: no gain (profiles/)
     p->last_rec_kernel = 1;
-    auto kern = k_rec3_fused<T, L, T2, NT, R2, MINB>;
+    auto kern = k_rec3_fused<T, L, T2, NT, R2, MINB, EDGE>;
     NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));   // per-device attribute: set on every launch
     const FusedTaps<T, L> tp = make_taps<T, L>(p, true);
     const int64_t grid = (int64_t)prm.tiles1 * prm.tiles2 * prm.nchunks * batches;
@@ -1824,6 +1835,9 @@ static int launch_rec3_bulk_any(nddwt_plan *p, const Rec3Params<T> &prm, cudaStr
 template <typename T, int L>
 static int launch_rec3_any(nddwt_plan *p, const Rec3Params<T> &prm, cudaStream_t s)
 {
+    // rows that are not 16-byte multiples (odd n1: 131 x 128 x 30 of mex/mex_test.m:84): direct element loads and
+    // element-wise guarded stores -- the staged kernels need 16-byte aligned rows for their bulk copies
+    if (prm.n1 % (16 / (int)sizeof(T)) != 0) return launch_rec3_v<T, L, 16, 320, 8, 2, 1>(p, prm, s);
     if constexpr (sizeof(T) == 8) {
         if (tuning_variant() / 100 % 10 != 9) {
             const int rc = launch_rec3_rows<T, L>(p, prm, s);
@@ -2134,13 +2148,19 @@ static bool fused_ranges_ok(const nddwt_plan *p)
     return tiles * ((p->dims[2] + 3) / 4) * batches < (int64_t)0x7fffffff;
 }
 
+static bool rows_unaligned(const nddwt_plan *p) { return p->dims[0] % (16 / (int64_t)p->esize) != 0; }
+// analysis with rows that are not 16-byte multiples has no shrink epilogue: such plans take the generic kernels + in-place pass
+static bool dec_rows_ok(const nddwt_plan *p) { return !(p->shrink_mode && rows_unaligned(p)); }
+
 static bool fused_geometry_ok(const nddwt_plan *p)
 {
     if (p->ndims < 3 || p->batch != 1) return false;
     if (!fused_ranges_ok(p)) return false;
     const int FL = fused_L(p, false);
     if (FL == 0 || p->dims[0] < FL || p->dims[1] < FL) return false;
-    if (p->dims[0] % (16 / (int64_t)p->esize) != 0) return false;   // 16-byte rows (vector stores, bulk copies)
+    // 4-D: the last-dim passes move 16-byte chunks of the hyperplane; rows themselves may be odd (element-wise
+    // tile-kernel instantiations)
+    if (p->ndims == 4 && (p->dims[0] * p->dims[1] * p->dims[2]) % (16 / (int64_t)p->esize) != 0) return false;
     return true;
 }
 
@@ -2236,6 +2256,7 @@ int accumulate_planes(nddwt_plan *p, const AccParams &prm, int64_t plane_elems, 
 bool fused_is_separable(const nddwt_plan *p)
 {
     if (p->kernel_mode != 0 || p->batch != 1 || p->ndims != 4 || !uniform_taps(p) || !fused_geometry_ok(p)) return false;
+    if (rows_unaligned(p)) return false;      // multi-GPU part-wise schedule: aligned rows only
     for (int j = 0; j < NDDWT_MAX_LEVELS; ++j)
         if (p->dil[j] != 1) return false;
     return p->L[0] == 2 || p->L[0] == 4 || p->L[0] == 6 || p->L[0] == 8;
@@ -2245,7 +2266,7 @@ bool fused_is_separable(const nddwt_plan *p)
 int fused_dec_level_part(nddwt_plan *p, int dil, int part, const void *a_in, const LevelIO &io,
                          void *const *out_bands, cudaStream_t s, const ZRange &zr)
 {
-    if (dil != 1 || !uniform_taps(p) || p->ndims != 4 || !fused_geometry_ok(p)) return 1;
+    if (dil != 1 || !uniform_taps(p) || p->ndims != 4 || !fused_geometry_ok(p) || !dec_rows_ok(p)) return 1;
     NDDWT_T_SWITCH(p, (dispatch_dec4<TT>(p, a_in, io, out_bands, s, part, zr)));
 }
 
@@ -2260,11 +2281,10 @@ int fused_dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io,
                     cudaStream_t s)
 {
     const int FL = fused_L(p, io.halo_lo != nullptr || io.halo_hi != nullptr);
-    if (dil != 1 || FL == 0) return 1;
+    if (dil != 1 || FL == 0 || !dec_rows_ok(p)) return 1;
     if (p->ndims == 3) {
         if (!fused_ranges_ok(p)) return 1;
         if (p->dims[0] < FL || p->dims[1] < FL) return 1;
-        if (p->dims[0] % (16 / (int64_t)p->esize) != 0) return 1;   // 16-byte row alignment for the vector stores
         switch (p->dtype) {
             case NDDWT_C64: return dispatch_dec3<float2>(p, FL, a_in, io, out_bands, s);
             case NDDWT_F32: return dispatch_dec3<float>(p, FL, a_in, io, out_bands, s);
@@ -2285,7 +2305,6 @@ int fused_rec_level(nddwt_plan *p, int dil, const void *const *in_bands, void *a
     if (p->ndims == 3) {
         if (!fused_ranges_ok(p)) return 1;
         if (p->dims[0] < FL || p->dims[1] < FL) return 1;
-        if (p->dims[0] % (16 / (int64_t)p->esize) != 0) return 1;
         switch (p->dtype) {
             case NDDWT_C64: return dispatch_rec3<float2>(p, FL, in_bands, a_out, s);
             case NDDWT_F32: return dispatch_rec3<float>(p, FL, in_bands, a_out, s);

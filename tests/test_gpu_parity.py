@@ -100,7 +100,9 @@ def test_parity_vs_oracle(sizes, wn, level, l2, dtype):
     ((256, 256), ["db1", "db4"], 2, 1),                        # example_nd_dwt_2D.m:5-8
     ((48, 40, 24), ["db4", "db2", "db3"], 2, 1),
     ((64, 64, 20), ["db1", "db3", "db9"], 2, 0),               # db9 exceeds the register ring: generic kernels
-    ((131, 128, 30), "db3", 2, 0),                             # odd rows (no 16-byte alignment): generic kernels
+    ((131, 128, 30), "db3", 2, 1),                             # mex/mex_test.m:84: odd rows -> element-wise tile-kernel instantiations
+    ((33, 24, 10, 8), "db2", 2, 1),                            # 4-D, odd rows, hyperplane still a 16-byte multiple
+    ((33, 25, 9, 8), "db2", 1, 0),                             # 4-D, all-odd hyperplane: generic kernels
 ])
 def test_reference_shapes_kernel_family_and_parity(sizes, wn, level, fused):
     """The reference's own test shapes with MIXED wavelets run the fused kernels (the shorter filters are
@@ -223,6 +225,30 @@ def test_linearity_and_shift_equivariance_full_size():
     o2 = nd.nd_dwt_3D("db4", [n, n, n], "precision", "single", "compute", "gpu", "pres_l2_norm", 1)
     y2 = o2.dec(a, 3)
     assert abs(float(torch.linalg.vector_norm(y2) / torch.linalg.vector_norm(a)) - 1) <= 1e-4
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64", "complex64", "complex128"])
+@pytest.mark.parametrize("sizes,wn,level", [((131, 70, 30), "db4", 2), ((67, 41, 12, 6), "db3", 2), ((35, 33, 20), ["db1", "db4", "db2"], 2)])
+def test_odd_row_lengths_fused(sizes, wn, level, dtype):
+    """Rows that are not 16-byte multiples in 3-D / 4-D: element-wise instantiations of the tile kernels, every dtype
+    (complex double rows are always 16-byte multiples and take the normal path)."""
+    prec = _prec(dtype)
+    x = orc.synth(sizes, dtype, 14)
+    a = _obj(sizes, wn, 0, prec)
+    wide = np.complex128 if np.iscomplexobj(x) else np.float64
+    y = a.dec(x, level)
+    assert a._plan(np.iscomplexobj(x), 0).last_path == 1
+    assert orc.rel_l2(y, orc.dec_direct(x.astype(wide), wn, level)) <= TOL[prec]
+    c = orc.synth(y.shape, dtype, 15)
+    assert orc.rel_l2(a.rec(c), orc.rec_direct(c.astype(wide), wn, False)) <= TOL[prec]
+    assert a._plan(np.iscomplexobj(x), 0).last_path == 1
+    assert orc.rel_l2(a.rec(y), x) <= TOL[prec]
+    # the fused shrink has no element-wise instantiation: such plans fall back to the generic kernels + in-place pass
+    if dtype == "complex64":
+        tab = np.full((level, 1 << len(sizes)), 0.3)
+        a.set_shrink(tab)
+        ys = a.dec(x, level)
+        assert orc.rel_l2(ys, orc.shrink_soft(orc.dec_direct(x.astype(wide), wn, level), tab, len(sizes))) <= TOL[prec]
 
 
 def test_cfg3_full_size_vs_oracle():
