@@ -113,7 +113,9 @@ NDDWT_API int64_t nddwt_plan_launch_count(const nddwt_plan *plan);
  * a multi-GPU plan).  Reading synchronises and clears that kind. */
 NDDWT_API int nddwt_plan_profile(nddwt_plan *plan, int on);
 NDDWT_API int nddwt_plan_kernel_time(nddwt_plan *plan, int kind, double *total_ms, int64_t *count);
-/* 1 if the last dec/rec of this plan ran the fused kernels, 0 if the generic ones. */
+/* Kernel family of the last dec/rec level of this plan: 1 = fused level kernels, 2 = hybrid (generic separable passes
+ * along the outer dimensions, the fused 2-D kernels over all (dim 1, dim 2) planes: db5..db10 in 3-D/4-D, batched 2-D..4-D
+ * arrays), 0 = generic separable passes only (a-trous dilation, forced by nddwt_plan_set_kernel_mode). */
 NDDWT_API int nddwt_plan_last_path(const nddwt_plan *plan);
 /* Which synthesis tile kernel the last fused 3-D/4-D level of this plan launched (tests and profiles):
  * 0 none yet, 1 direct-load tiles (k_rec3_fused), 2 TMA-staged 32-column tiles (k_rec3_bulk),

@@ -58,9 +58,10 @@ static int dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io
         rc = fused2d_dec_level(p, dil, a_in, io, out_bands, s);
         if (rc <= 0) { p->last_path = 1; return rc; }
     }
-    p->last_path = 0;
+    p->hybrid_used = false;
     int rc = generic_dec_level(p, dil, a_in, io, out_bands, s);
-    if (rc || !p->shrink_mode) return rc;
+    p->last_path = p->hybrid_used ? 2 : 0;
+    if (rc || !p->shrink_mode || p->hybrid_used) return rc;      // the hybrid path thresholds in the 2-D kernels' stores
     // no fused epilogue on this path: threshold the detail bands in place
     const int j = p->cur_level >= 1 && p->cur_level <= NDDWT_MAX_LEVELS ? p->cur_level : 1;
     for (int b = 1; b < (1 << p->ndims) && !rc; ++b) rc = shrink_band(p, out_bands[b], p->numel, p->shrink_thr[j - 1][b], s);
@@ -75,8 +76,10 @@ static int rec_level(nddwt_plan *p, int dil, const void *const *in_bands, void *
         rc = fused2d_rec_level(p, dil, in_bands, a_out, s);
         if (rc <= 0) { p->last_path = 1; return rc; }
     }
-    p->last_path = 0;
-    return generic_rec_level(p, dil, in_bands, a_out, s);
+    p->hybrid_used = false;
+    const int rc = generic_rec_level(p, dil, in_bands, a_out, s);
+    p->last_path = p->hybrid_used ? 2 : 0;
+    return rc;
 }
 
 static int check_level(const nddwt_plan *p, int level)

@@ -5,6 +5,7 @@
 // and nd_dwt_dec_1level / nd_dwt_rec_1level (mex/nddwt.c:98-186) for num_dims == 2.
 // Any tap length (db1..db10), any of the four element types, any (odd) sizes; mixed wavelets run with the
 // longer tap length, the shorter filter zero-padded symmetrically (same phase, same result).
+#include <algorithm>
 #include "nddwt_plan.h"
 
 namespace nddwt {
@@ -27,6 +28,10 @@ __global__ void __launch_bounds__(NT)
 k_dec2_fused(const T *__restrict__ in, T *__restrict__ o0, T *__restrict__ o1, T *__restrict__ o2,
              T *__restrict__ o3, int n1, int n2, const Taps2<T, L> tp)
 {
+    {   // blockIdx.z: independent planes of a 3-D / 4-D / batched array (hybrid path: outer dims by the generic passes)
+        const int64_t po = (int64_t)blockIdx.z * n1 * n2;
+        in += po; o0 += po; o1 += po; o2 += po; o3 += po;
+    }
     constexpr int H = L - 1, HB = L / 2 - 1;          // analysis reads n-(L/2-1) .. n+L/2
     constexpr int W1 = TX + H, W2 = TY + H, P = W1 | 1;   // odd pitch
     extern __shared__ __align__(16) unsigned char smem2_raw[];
@@ -79,6 +84,10 @@ __global__ void __launch_bounds__(NT)
 k_rec2_fused(const T *__restrict__ c0, const T *__restrict__ c1, const T *__restrict__ c2,
              const T *__restrict__ c3, T *__restrict__ out, int n1, int n2, const Taps2<T, L> tp)
 {
+    {
+        const int64_t po = (int64_t)blockIdx.z * n1 * n2;
+        c0 += po; c1 += po; c2 += po; c3 += po; out += po;
+    }
     constexpr int H = L - 1, HB = L / 2;              // synthesis reads n-L/2 .. n+L/2-1
     constexpr int W1 = TX + H, W2 = TY + H, P = W1 | 1;
     extern __shared__ __align__(16) unsigned char smem2_raw[];
@@ -121,7 +130,7 @@ k_rec2_fused(const T *__restrict__ c0, const T *__restrict__ c1, const T *__rest
 }
 
 template <typename T, int L>
-static Taps2<T, L> make_taps2(const nddwt_plan *p, bool rec)
+static Taps2<T, L> make_taps2(const nddwt_plan *p, bool rec, int band0 = 0)
 {
     using R = typename Elem<T>::R;
     Taps2<T, L> t;
@@ -132,47 +141,58 @@ static Taps2<T, L> make_taps2(const nddwt_plan *p, bool rec)
             t.hi[d][k] = (R)padded_tap(src.d[d].hi, p->L[d], L, k);
         }
     const int j = p->cur_level >= 1 && p->cur_level <= NDDWT_MAX_LEVELS ? p->cur_level : 1;
-    for (int b = 0; b < 4; ++b) t.thr[b] = (R)((!rec && p->shrink_mode) ? p->shrink_thr[j - 1][b] : 0.0);
+    for (int b = 0; b < 4; ++b) t.thr[b] = (R)((!rec && p->shrink_mode) ? p->shrink_thr[j - 1][band0 + b] : 0.0);
     return t;
 }
 
 template <typename T, int L>
-static int launch_dec2(nddwt_plan *p, const void *a_in, void *const *out_bands, cudaStream_t s)
+static int launch_dec2(nddwt_plan *p, const void *a_in, void *const *out_bands, cudaStream_t s, int64_t planes = 1,
+                       int band0 = 0)
 {
     constexpr int TX = 32, TY = 16, NT = 256, H = L - 1, P = (TX + H) | 1;
     const int n1 = (int)p->dims[0], n2 = (int)p->dims[1];
     const size_t smem = (size_t)((TY + H) * P + 2 * TY * P) * sizeof(T);
     auto kern = k_dec2_fused<T, L, TX, TY, NT>;
     NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per-device attribute: set on every launch
-    dim3 grid((n1 + TX - 1) / TX, (n2 + TY - 1) / TY);
-    {
-        LaunchTimer lt(p, KIND_DEC3, s);
-        kern<<<grid, NT, smem, s>>>(reinterpret_cast<const T *>(a_in), reinterpret_cast<T *>(out_bands[0]),
-                                    reinterpret_cast<T *>(out_bands[1]), reinterpret_cast<T *>(out_bands[2]),
-                                    reinterpret_cast<T *>(out_bands[3]), n1, n2, make_taps2<T, L>(p, false));
+    const Taps2<T, L> tp = make_taps2<T, L>(p, false, band0);
+    const int64_t ps = (int64_t)n1 * n2;
+    for (int64_t z0 = 0; z0 < planes; z0 += 65535) {        // grid.z limit
+        const unsigned nz = (unsigned)std::min<int64_t>(65535, planes - z0);
+        dim3 grid((n1 + TX - 1) / TX, (n2 + TY - 1) / TY, nz);
+        {
+            LaunchTimer lt(p, KIND_DEC3, s);
+            kern<<<grid, NT, smem, s>>>(reinterpret_cast<const T *>(a_in) + z0 * ps, reinterpret_cast<T *>(out_bands[0]) + z0 * ps,
+                                        reinterpret_cast<T *>(out_bands[1]) + z0 * ps, reinterpret_cast<T *>(out_bands[2]) + z0 * ps,
+                                        reinterpret_cast<T *>(out_bands[3]) + z0 * ps, n1, n2, tp);
+        }
+        p->launches++;
+        NDDWT_CUDA(cudaGetLastError());
     }
-    p->launches++;
-    NDDWT_CUDA(cudaGetLastError());
     return 0;
 }
 
 template <typename T, int L>
-static int launch_rec2(nddwt_plan *p, const void *const *in_bands, void *a_out, cudaStream_t s)
+static int launch_rec2(nddwt_plan *p, const void *const *in_bands, void *a_out, cudaStream_t s, int64_t planes = 1)
 {
     constexpr int TX = 32, TY = 16, NT = 256, H = L - 1, P = (TX + H) | 1;
     const int n1 = (int)p->dims[0], n2 = (int)p->dims[1];
     const size_t smem = (size_t)(4 * (TY + H) * P + 2 * TY * P) * sizeof(T);
     auto kern = k_rec2_fused<T, L, TX, TY, NT>;
     NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per-device attribute: set on every launch
-    dim3 grid((n1 + TX - 1) / TX, (n2 + TY - 1) / TY);
-    {
-        LaunchTimer lt(p, KIND_REC3, s);
-        kern<<<grid, NT, smem, s>>>(reinterpret_cast<const T *>(in_bands[0]), reinterpret_cast<const T *>(in_bands[1]),
-                                    reinterpret_cast<const T *>(in_bands[2]), reinterpret_cast<const T *>(in_bands[3]),
-                                    reinterpret_cast<T *>(a_out), n1, n2, make_taps2<T, L>(p, true));
+    const Taps2<T, L> tp = make_taps2<T, L>(p, true);
+    const int64_t ps = (int64_t)n1 * n2;
+    for (int64_t z0 = 0; z0 < planes; z0 += 65535) {
+        const unsigned nz = (unsigned)std::min<int64_t>(65535, planes - z0);
+        dim3 grid((n1 + TX - 1) / TX, (n2 + TY - 1) / TY, nz);
+        {
+            LaunchTimer lt(p, KIND_REC3, s);
+            kern<<<grid, NT, smem, s>>>(reinterpret_cast<const T *>(in_bands[0]) + z0 * ps, reinterpret_cast<const T *>(in_bands[1]) + z0 * ps,
+                                        reinterpret_cast<const T *>(in_bands[2]) + z0 * ps, reinterpret_cast<const T *>(in_bands[3]) + z0 * ps,
+                                        reinterpret_cast<T *>(a_out) + z0 * ps, n1, n2, tp);
+        }
+        p->launches++;
+        NDDWT_CUDA(cudaGetLastError());
     }
-    p->launches++;
-    NDDWT_CUDA(cudaGetLastError());
     return 0;
 }
 
@@ -191,21 +211,59 @@ static int launch_rec2(nddwt_plan *p, const void *const *in_bands, void *a_out, 
         default: return 1;                                 \
     }
 
+static int taps2d(const nddwt_plan *p) { return p->L[0] > p->L[1] ? p->L[0] : p->L[1]; }   // dims 1, 2 only
+
 template <typename T>
-static int dispatch_dec2(nddwt_plan *p, const void *a_in, void *const *out_bands, cudaStream_t s)
+static int dispatch_dec2(nddwt_plan *p, const void *a_in, void *const *out_bands, cudaStream_t s, int64_t planes = 1,
+                         int band0 = 0)
 {
-    NDDWT2_L_SWITCH(plan_max_taps(p), (launch_dec2<T, LL>(p, a_in, out_bands, s)));
+    NDDWT2_L_SWITCH(taps2d(p), (launch_dec2<T, LL>(p, a_in, out_bands, s, planes, band0)));
 }
 template <typename T>
-static int dispatch_rec2(nddwt_plan *p, const void *const *in_bands, void *a_out, cudaStream_t s)
+static int dispatch_rec2(nddwt_plan *p, const void *const *in_bands, void *a_out, cudaStream_t s, int64_t planes = 1)
 {
-    NDDWT2_L_SWITCH(plan_max_taps(p), (launch_rec2<T, LL>(p, in_bands, a_out, s)));
+    NDDWT2_L_SWITCH(taps2d(p), (launch_rec2<T, LL>(p, in_bands, a_out, s, planes)));
+}
+
+static bool ok2d_geometry(const nddwt_plan *p)
+{
+    if (p->ndims < 2) return false;
+    if (p->dims[0] < taps2d(p) || p->dims[1] < taps2d(p)) return false;
+    if (p->dims[0] > 0x7fffffff - 64 || p->dims[1] > (int64_t)65535 * 16) return false;
+    return p->dims[0] * p->dims[1] < ((int64_t)1 << 31);
+}
+
+// Hybrid path of 3-D / 4-D / batched arrays whose outer dimensions the tile kernels do not take (db5..db10, batches):
+// `planes` independent (dim 1, dim 2) planes through the fused 2-D kernels; the caller (nddwt_generic.cu) has filtered
+// the outer dimensions with the generic passes.  band0: index of out_bands[0] within the level (thresholds).
+int fused2d_dec_planes(nddwt_plan *p, const void *a_in, void *const *out_bands, int64_t planes, int band0, cudaStream_t s)
+{
+    if (!ok2d_geometry(p)) return 1;
+    switch (p->dtype) {
+        case NDDWT_F32: return dispatch_dec2<float>(p, a_in, out_bands, s, planes, band0);
+        case NDDWT_F64: return dispatch_dec2<double>(p, a_in, out_bands, s, planes, band0);
+        case NDDWT_C64: return dispatch_dec2<float2>(p, a_in, out_bands, s, planes, band0);
+        case NDDWT_C128: return dispatch_dec2<double2>(p, a_in, out_bands, s, planes, band0);
+    }
+    return 1;
+}
+
+int fused2d_rec_planes(nddwt_plan *p, const void *const *in_bands, void *a_out, int64_t planes, cudaStream_t s)
+{
+    if (!ok2d_geometry(p)) return 1;
+    switch (p->dtype) {
+        case NDDWT_F32: return dispatch_rec2<float>(p, in_bands, a_out, s, planes);
+        case NDDWT_F64: return dispatch_rec2<double>(p, in_bands, a_out, s, planes);
+        case NDDWT_C64: return dispatch_rec2<float2>(p, in_bands, a_out, s, planes);
+        case NDDWT_C128: return dispatch_rec2<double2>(p, in_bands, a_out, s, planes);
+    }
+    return 1;
 }
 
 static bool ok2d(const nddwt_plan *p, int dil, const LevelIO *io)
 {
     if (dil != 1 || p->ndims != 2 || p->batch != 1) return false;
-    if (p->dims[0] < plan_max_taps(p) || p->dims[1] < plan_max_taps(p)) return false;
+    if (p->dims[0] < taps2d(p) || p->dims[1] < taps2d(p)) return false;
     if (io && (io->halo_lo || io->halo_hi)) return false;      // slabs of 2-D arrays use the generic kernels
     // launch geometry: dims are ints in the kernels, grid.y = ceil(n2 / 16) must stay <= 65535
     if (p->dims[0] > 0x7fffffff - 64 || p->dims[1] > (int64_t)65535 * 16) return false;

@@ -169,6 +169,13 @@ static int dec_recurse(nddwt_plan *p, int k, int dil, const T *in, const LevelIO
     const bool last = (k == p->ndims - 1);
     const T *hl = last ? reinterpret_cast<const T *>(io.halo_lo) : nullptr;
     const T *hh = last ? reinterpret_cast<const T *>(io.halo_hi) : nullptr;
+    // hybrid: dims 1 and 2 of every remaining plane in one fused 2-D launch (4 bands written once) instead of two more
+    // generic passes with their intermediates; the outer dims were filtered by the passes above
+    if (k == 1 && dil == 1 && p->kernel_mode == 0 && !(last && (hl || hh))) {
+        const int64_t planes = p->numel / (p->dims[0] * p->dims[1]);
+        const int rc = fused2d_dec_planes(p, in, out_bands + idx * 4, planes, idx * 4, s);
+        if (rc <= 0) { p->hybrid_used = true; return rc; }
+    }
     if (k == 0) {
         return launch_dec_dim<T>(p, 0, dil, in, hl, hh, reinterpret_cast<T *>(out_bands[idx * 2 + 0]),
                                  reinterpret_cast<T *>(out_bands[idx * 2 + 1]), s);
@@ -187,6 +194,11 @@ static int dec_recurse(nddwt_plan *p, int k, int dil, const T *in, const LevelIO
 template <typename T>
 static int rec_recurse(nddwt_plan *p, int k, int dil, int idx, const void *const *bands, T *dst, cudaStream_t s)
 {
+    if (k == 2 && dil == 1 && p->kernel_mode == 0) {      // hybrid: dims 1, 2 by the fused 2-D kernels
+        const int64_t planes = p->numel / (p->dims[0] * p->dims[1]);
+        const int rc = fused2d_rec_planes(p, bands + idx * 4, dst, planes, s);
+        if (rc <= 0) { p->hybrid_used = true; return rc; }
+    }
     // operands S(k-1, 2 idx) and S(k-1, 2 idx + 1)
     const T *lo, *hi;
     if (k == 1) {

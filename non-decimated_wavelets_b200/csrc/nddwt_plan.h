@@ -27,7 +27,8 @@ struct nddwt_plan {
 
     int dil[NDDWT_MAX_LEVELS];
     int kernel_mode = 0;   // 0 auto, 1 generic only
-    int last_path = 0;     // 1 fused, 0 generic
+    int last_path = 0;     // 1 fused, 0 generic, 2 hybrid (generic passes for the outer dims + fused 2-D kernels over the planes)
+    bool hybrid_used = false;
     int last_rec_kernel = 0;   // synthesis tile kernel of the last 3-D/4-D fused level: 1 direct-load, 2 bulk (32-column tiles), 4 full rows
     int64_t launches = 0;
     // fused coefficient shrink (nddwt_plan_set_shrink): soft threshold applied to the detail bands as the
@@ -122,6 +123,8 @@ int fused_rec_stage2(nddwt_plan *p, int dil, const void *u_lo, const void *u_hi,
 int fused2d_dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io, void *const *out_bands,
                       cudaStream_t s);
 int fused2d_rec_level(nddwt_plan *p, int dil, const void *const *in_bands, void *a_out, cudaStream_t s);
+int fused2d_dec_planes(nddwt_plan *p, const void *a_in, void *const *out_bands, int64_t planes, int band0, cudaStream_t s);
+int fused2d_rec_planes(nddwt_plan *p, const void *const *in_bands, void *a_out, int64_t planes, cudaStream_t s);
 int fused1d_transform(nddwt_plan *p, bool rec, const void *in, void *out, int level, cudaStream_t s);
 bool fused_is_separable(const nddwt_plan *p);
 int fused_rec_stage2_scatter(nddwt_plan *p, int dil, const void *u_lo, const void *u_hi, void *out, void *over_lo,

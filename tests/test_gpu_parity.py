@@ -99,14 +99,17 @@ def test_parity_vs_oracle(sizes, wn, level, l2, dtype):
     ((264, 264), ["db1", "db3"], 1, 1),                        # Test/nddwt2D_test.m:5-8
     ((256, 256), ["db1", "db4"], 2, 1),                        # example_nd_dwt_2D.m:5-8
     ((48, 40, 24), ["db4", "db2", "db3"], 2, 1),
-    ((64, 64, 20), ["db1", "db3", "db9"], 2, 0),               # db9 exceeds the register ring: generic kernels
+    ((64, 64, 20), ["db1", "db3", "db9"], 2, 2),               # Test: db9 exceeds the register ring -> hybrid: generic pass along dim 3, fused 2-D kernels over the planes
+    ((32, 32, 16, 16), ["db1", "db3", "db3", "db5"], 2, 2),    # SURVEY 8c shape: db5 along dim 4 -> hybrid
+    ((40, 36, 24), "db7", 2, 2),                               # long filters everywhere -> hybrid
     ((131, 128, 30), "db3", 2, 1),                             # mex/mex_test.m:84: odd rows -> element-wise tile-kernel instantiations
     ((33, 24, 10, 8), "db2", 2, 1),                            # 4-D, odd rows, hyperplane still a 16-byte multiple
-    ((33, 25, 9, 8), "db2", 1, 0),                             # 4-D, all-odd hyperplane: generic kernels
+    ((33, 25, 9, 8), "db2", 1, 2),                             # 4-D, all-odd hyperplane: no 16-byte last-dim passes -> hybrid
 ])
 def test_reference_shapes_kernel_family_and_parity(sizes, wn, level, fused):
     """The reference's own test shapes with MIXED wavelets run the fused kernels (the shorter filters are
-    zero-padded to the longest tap length, which keeps their phase) and equal the generic kernels and the oracle."""
+    zero-padded to the longest tap length, which keeps their phase) and equal the generic kernels and the oracle.
+    fused: 1 = fused tile kernels, 2 = hybrid (generic passes along the outer dims, fused 2-D kernels over the planes)."""
     x = orc.synth(sizes, np.complex64, 8)
     a = _obj(sizes, wn, 1, "single", kernel_mode=0)
     b = _obj(sizes, wn, 1, "single", kernel_mode=1)
