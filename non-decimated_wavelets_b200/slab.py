@@ -390,24 +390,48 @@ class PeerSlabTransform:
     transport = "peer-memory pushes (CUDA IPC + copy engines), flags in peer memory"
 
     def __init__(self, sizes, wnames, dtype_code, pres_l2_norm, rank, world, device_index, group=None, dilations=None):
-        from ._lib import MultiPlan
+        from ._lib import MultiPlan, lib
+        import ctypes
         self.sizes = tuple(int(s) for s in sizes)
         self.d = len(self.sizes)
         self.rank, self.world, self.device_index = rank, world, device_index
-        self.plan = MultiPlan(self.sizes, wnames, dtype_code, pres_l2_norm, rank=rank, world=world, device=device_index)
-        if dilations is not None:
-            self.plan.set_dilations(dilations)
+        # Every rank takes part in every collective below whatever happens locally, and all ranks fail together:
+        # a rank that cannot create or map its plan must not leave the others waiting in an all-gather.
+        err, blob = None, b""
+        try:
+            self.plan = MultiPlan(self.sizes, wnames, dtype_code, pres_l2_norm, rank=rank, world=world, device=device_index)
+            if dilations is not None:
+                self.plan.set_dilations(dilations)
+            n = int(lib().nddwt_mplan_export_size())
+            buf = (ctypes.c_char * n)()
+            from ._lib import check
+            check(lib().nddwt_mplan_export(self.plan.handle, buf))
+            blob = bytes(buf)
+        except Exception as exc:   # noqa: BLE001
+            err = "rank %d: %s" % (rank, str(exc)[:200])
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, (err, blob), group=group)
+            errs = [e for e, _ in gathered if e]
+            if not errs:
+                try:
+                    joined = b"".join(b for _, b in gathered)
+                    cbuf = (ctypes.c_char * len(joined)).from_buffer_copy(joined)
+                    check(lib().nddwt_mplan_import(self.plan.handle, cbuf))
+                except Exception as exc:   # noqa: BLE001
+                    err = "rank %d: %s" % (rank, str(exc)[:200])
+                gathered = [None] * world
+                dist.all_gather_object(gathered, err, group=group)
+                errs = [e for e in gathered if e]
+            if errs:
+                raise RuntimeError("peer-memory plan could not be set up: " + "; ".join(errs))
+        elif err:
+            raise RuntimeError(err)
         self.start, self.n_local = self.plan.slab(rank)
         self.parts = [self.plan.slab(r) for r in range(world)]
         self.local_shape = (self.n_local,) + tuple(reversed(self.sizes[:-1]))
         self.overlap = self.plan.separable
         self.scatter = self.plan.separable
-        if world > 1:
-            def all_gather(blob):
-                out = [None] * world
-                dist.all_gather_object(out, blob, group=group)
-                return out
-            self.plan.connect(all_gather)
 
     def num_bands(self, level):
         nd = 1 << self.d
