@@ -253,6 +253,7 @@ def run_multi(args, wl_name, wl):
     l0 = plan.launches
     hb0 = plan.halo_bytes if transport == "peer" else 0
     ms_per_step = _time_pairs(tr, x, y, xr, level, args.steps, 0, dev)
+    hb1 = plan.halo_bytes if transport == "peer" else 0
     clocks = sampler.stop() if sampler else None
     launches = plan.launches - l0
     # per-kind device times of this rank (events around every launch, second pass; not part of the timed value)
@@ -288,7 +289,7 @@ def run_multi(args, wl_name, wl):
     pair_gbs = pair_bytes / (ms_per_step * 1e-3) / 1e9
     plane_bytes = int(np.prod(sizes[:-1])) * esize
     if transport == "peer":
-        halo_bytes = (plan.halo_bytes - hb0) // max(args.steps, 1)
+        halo_bytes = (hb1 - hb0) // max(args.steps, 1)
         timeouts = plan.wait_timeouts
     else:
         halo_bytes = level * (L - 1) * plane_bytes * (2 if getattr(tr, "scatter", False) else 3)
