@@ -1808,6 +1808,7 @@ static int launch_rec3_rows(nddwt_plan *p, const Rec3Params<T> &prm, cudaStream_
     // correct on every test shape and slower: 3.86 vs 3.75 ms on cfg5 (profiles/r02_variants.md); removed.
     if (prm.n1 == 192) return launch_rec3_rows_n<T, L, 8, 384, 2, 192>(p, prm, s);
     if (prm.n1 == 256) return launch_rec3_rows_n<T, L, 8, 512, 2, 256>(p, prm, s);   // 2-stage ring (224 KB), 128-register cap
+    if (prm.n1 > 192) return launch_rec3_rows_n<T, L, 8, 512, 2, 0>(p, prm, s);      // rows of 196..252 elements
     return launch_rec3_rows_n<T, L, 8, 384, 2, 0>(p, prm, s);
 }
 

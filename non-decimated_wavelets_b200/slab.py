@@ -92,9 +92,6 @@ class HaloExchanger:
     def exchange(self, local, halo_lo, halo_hi):
         """local: [n_local, ...] contiguous; halo_lo: [below, ...]; halo_hi: [above, ...] (filled in place).
         Planes a rank needs from itself are copied locally."""
-        import os
-        if os.environ.get("NDDWT_SLAB_NOCOMM") == "1":     # timing experiment only (results are wrong)
-            return
         ops, pending_self = [], []
         for which, runs, dst in ((0, self.recv_lo, halo_lo), (1, self.recv_hi, halo_hi)):
             for k, (o, idx, cnt, off) in enumerate(runs):
@@ -191,7 +188,7 @@ class SlabTransform:
     is [nb, n_local, ...] with the reference's band order (deepest level first)."""
 
     def __init__(self, sizes, wnames, level_max, engine, taps_last, rank, world, group=None, device="cpu",
-                 dtype=None):
+                 dtype=None, overlap=True, scatter=True):
         self.sizes = tuple(int(s) for s in sizes)
         self.d = len(self.sizes)
         self.rank, self.world, self.group = rank, world, group
@@ -211,15 +208,14 @@ class SlabTransform:
         self.approx = [torch.empty(self.local_shape, dtype=dtype, device=device) for _ in range(2)]
         self.u = [torch.empty(self.local_shape, dtype=dtype, device=device) for _ in range(2)]
         # overlap of exchange and compute: needs the part-wise engine entry points, CUDA tensors and >1 rank
-        import os
         self.overlap = (world > 1 and getattr(engine, "separable", False) and torch.device(device).type == "cuda"
-                        and os.environ.get("NDDWT_SLAB_OVERLAP", "1") != "0")
+                        and bool(overlap))
         if self.overlap:
             self.comm_stream = torch.cuda.Stream(device=device, priority=-1)
             self.u_hi2 = [self.u[1], torch.empty(self.local_shape, dtype=dtype, device=device)]
             self.h_rec2 = [self.h_rec, (mk(self.L // 2, 2), mk(self.L // 2 - 1, 2))]
             # scatter-form synthesis exchange: overhang partial sums (same plane sets as the analysis halos)
-            self.scatter = os.environ.get("NDDWT_SLAB_SCATTER", "1") != "0"
+            self.scatter = bool(scatter)
             self.over = (mk(lo_d), mk(hi_d))
             self.stage = mk(self.x_dec.stage_planes)
 

@@ -405,7 +405,7 @@ def test_fused_1d_cascade(n, wn, level, dtype):
 
 @pytest.mark.parametrize("wn,dtype", [("db1", "complex64"), ("db2", "complex64"), ("db3", "complex64"), ("db4", "complex64"),
                                       ("db2", "float64"), ("db4", "float64")])
-@pytest.mark.parametrize("sizes,level", [((64, 30, 9, 8), 1), ((192, 40, 16, 8), 1), ((72, 20, 8, 8), 1),
+@pytest.mark.parametrize("sizes,level", [((64, 30, 9, 8), 1), ((192, 40, 16, 8), 1), ((72, 20, 8, 8), 1), ((224, 24, 9, 8), 1),
                                           ((128, 17, 12), 1), ((32, 32, 24, 16), 2), ((64, 32, 12, 16), 2), ((256, 20, 8, 8), 1)])
 def test_full_row_synthesis_kernel(sizes, level, wn, dtype):
     """k_rec3_rows (full-row tiles, 8-byte elements) is chosen by default only for big 4-D batches; lower
