@@ -130,3 +130,21 @@ def test_multi_gpu_options_and_export_blob_size():
     assert np.array_equal(orc.shrink_soft(y, np.zeros((2, 4)), 2), y)
     ys = orc.shrink_soft(y, np.full((2, 4), 1e9), 2)
     assert np.array_equal(ys[..., 0], y[..., 0]) and not ys[..., 1:].any()
+
+
+def test_header_is_plain_c_and_every_entry_point_links(tmp_path):
+    """The drop-in boundary is a C ABI: include/nddwt_b200.h compiles as C99 (no C++-isms, no torch types) and a C
+    program that takes the address of every declared entry point links against libnddwt_b200.so."""
+    import subprocess
+    hdr = open(os.path.join(ROOT, "include", "nddwt_b200.h")).read()
+    names = sorted(set(re.findall(r"NDDWT_API[^;(]*?\b(nddwt_\w+)\s*\(", hdr)))
+    src = tmp_path / "abi_check.c"
+    src.write_text('#include "nddwt_b200.h"\n#include <stdio.h>\ntypedef void (*fn_t)(void);\nint main(void) {\n  fn_t fn[] = {\n'
+                   + "".join("    (fn_t)%s,\n" % n for n in names)
+                   + '  };\n  printf("%d entry points, %s\\n", (int)(sizeof fn / sizeof fn[0]), nddwt_version());\n  return 0;\n}\n')
+    libdir = os.path.dirname(nd.LIB_PATH)
+    exe = tmp_path / "abi_check"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-lnddwt_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    assert out.startswith("%d entry points" % len(names)) and "sm_100a" in out
