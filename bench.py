@@ -27,6 +27,7 @@ WORKLOADS = {
     # name: (sizes, wavelet, levels, dtype)        BASELINE.json configs
     "cfg1": ((256, 256), "db4", 3, "complex128"),
     "cfg2": ((65536,), "db8", 6, "complex64", 4096),    # 1-D batch: 4096 signals of 65536 samples (batch extension)
+    "cfg2q": ((65536,), "db8", 6, "complex64", 1024),   # a quarter of cfg2's batch (ncu captures)
     "cfg3": ((256, 256, 256), "db4", 3, "complex64"),
     "cfg4": ((256, 256, 256, 32), "db4", 3, "complex64"),
     "cfg4s8": ((256, 256, 256, 8), "db4", 3, "complex64"),   # one quarter of cfg4 along dim 4
@@ -354,11 +355,16 @@ def main():
     torch.cuda.synchronize()
     plan.profile(False)
     rec_kernel = {1: "k_rec3_fused", 2: "k_rec3_bulk", 4: "k_rec3_rows"}.get(plan.last_synthesis_kernel, "k_rec3")
-    kinds = ["analysis tile kernel k_dec3_fused", "synthesis tile kernel " + rec_kernel, "analysis last-dim pass k_dec_last",
+    dec_kernel = {1: "k_dec1_runs (1-D cascade, all levels)", 2: "k_dec2_fused"}.get(d, "k_dec3_fused")
+    if d <= 2:
+        rec_kernel = {1: "k_rec1_runs (1-D cascade, all levels)", 2: "k_rec2_fused"}[d]
+    kinds = ["analysis tile kernel " + dec_kernel, "synthesis tile kernel " + rec_kernel, "analysis last-dim pass k_dec_last",
              "synthesis last-dim pass k_rec_last", "generic separable pass"]
     # algorithmic bytes per launch of each kind: tile kernels move (1 + 2^3) arrays per
     # 3-D problem, i.e. (2 + 16) N e per launch in the 4-D batched form; last-dim passes 3 N e
-    per_launch = {0: ((1 + 8) if d == 3 else (2 + 16)) * nvox * esize, 1: ((8 + 1) if d == 3 else (16 + 2)) * nvox * esize,
+    # 2-D: (1 + 4) N e per level launch; 1-D: the whole J-level cascade is ONE launch, (1 + nb) N e
+    tile_arrays = {1: 1 + nb, 2: 1 + 4, 3: 1 + 8, 4: 2 + 16}[d]
+    per_launch = {0: tile_arrays * nvox * esize, 1: tile_arrays * nvox * esize,
                   2: 3 * nvox * esize, 3: 3 * nvox * esize, 4: 3 * nvox * esize}
     ktimes = {}
     for k in range(5):

@@ -1568,7 +1568,9 @@ static int launch_dec3_any(nddwt_plan *p, const Dec3Params<T> &prm, cudaStream_t
     // shrink epilogue: one-row stage-C runs keep it spill-free (two-row runs: 260 B of spills, 6.8 vs 4.4 ms on cfg5)
     if (p->shrink_mode) return launch_dec3_v<T, L, 16, 256, 1, 2, 0, 1, 1, 1>(p, prm, s);
     // (stage B shared evenly by all warps -- every thread half an item in the last half-iteration -- measured
-    // slower: 3.9-4.1 vs 3.65-3.7 ms, profiles/r02_variants.md)
+    // slower: 3.9-4.1 vs 3.65-3.7 ms; 32 x 32 tiles with one 512-thread CTA per SM (ring of 3 positions per thread,
+    // -11 % FMAs, -28 % shared-memory wavefronts): 3.95-3.99 ms with 2-row stage-C runs, 5.0-5.2 ms with 4-row runs
+    // (spills) vs 3.51-3.53 ms: profiles/r02_variants.md)
     return launch_dec3_v<T, L, 16, 256, 2, 2, 0, 1, 1>(p, prm, s);
 }
 

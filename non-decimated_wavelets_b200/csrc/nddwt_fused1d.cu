@@ -6,6 +6,7 @@
 // Replaces dec / rec / level_1_dec / level_1_rec of Functions/nd_dwt_1D.m:136-318 and
 // nd_dwt_dec / nd_dwt_rec (mex/nddwt.c:189-292) for num_dims == 1, for one signal or a batch of
 // signals (batch extension; BASELINE configs[1]: 4096 signals x 65536 samples, db8, 6 levels).
+#include <cstdlib>
 #include "nddwt_plan.h"
 
 namespace nddwt {
@@ -180,6 +181,239 @@ k_rec1_cascade(const T *__restrict__ coeffs, T *__restrict__ x, int64_t n1, int6
         if (t0 + o < n1) xs[t0 + o] = src[o];
 }
 
+
+// =============================================================================================
+// Round-2 cascade kernels ("runs"): the same one-launch J-level scheme, rebuilt around the two things that bound
+// the first version on BASELINE configs[1] (4096 x 65536, db8, J6, complex single: 5.5 + 8.9 ms against an FP32
+// floor of 2.9 + 2.9 ms): shared-memory wavefronts (9 / 18 16-byte loads per 2 outputs) and idle threads (a 2048 +
+// halo tile is 4.2 iterations of 256 threads x 2 outputs, i.e. 5).
+//   * a thread produces a RUN of R = CPT x VEC consecutive outputs per level with a sliding window of the
+//     source held in a static register ring (one 16-byte load per VEC outputs, the next chunk one step ahead);
+//     CPT is odd, so the lanes' 16-byte accesses (stride CPT chunks) are bank-conflict-free;
+//   * the tile length is chosen on the host so that the widest level is exactly `kit` full iterations of the CTA;
+//   * every level's buffer origin moves by the halo rounded up to whole 16-byte chunks (the window then starts
+//     SA / SR elements into its first chunk), so that shared and global accesses stay chunk-aligned at every level;
+//   * analysis: the detail outputs of a level are staged in shared memory (double-buffered) and leave as coalesced
+//     16-byte streaming stores while the next level computes;  synthesis: d_{j-1} is fetched by cp.async into the
+//     other detail buffer while level j computes (no exposed global latency per level).
+template <typename T, int L>
+struct Casc {
+    static constexpr int VEC = 16 / (int)sizeof(T);
+    static constexpr int HLS = L / 2 - 1;                               // analysis reads n-(L/2-1) .. n+L/2
+    static constexpr int HLSP = (HLS + VEC - 1) / VEC * VEC, SA = HLSP - HLS;
+    static constexpr int HALO_A = HLSP + L / 2;                         // buffer growth per analysis level
+    static constexpr int HLR = L / 2;                                   // synthesis reads n-L/2 .. n+L/2-1
+    static constexpr int HLRP = (HLR + VEC - 1) / VEC * VEC, SR = HLRP - HLR;
+    static constexpr int HALO_R = HLRP + L / 2 - 1;
+    static constexpr int WCH_A = (VEC - 1 + HALO_A) / VEC + 1;          // chunks under the window of one output chunk
+    static constexpr int WCH_R = (VEC - 1 + HALO_R) / VEC + 1;
+};
+
+template <int B>
+__device__ __forceinline__ void cp_async(void *smem, const void *gmem)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(sa), "l"(__cvta_generic_to_global(gmem)), "n"(B) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// asynchronous periodic copy global -> shared of `count` elements starting at global index `start` (any sign).
+// vec: start and n1 are multiples of VEC and src is 16-byte aligned -> whole chunks, none straddles the wrap.
+template <typename T, int NT>
+__device__ __forceinline__ void stage_wrapped(T *dst, const T *src, int64_t start, int count, int64_t n1, int tid, bool vec)
+{
+    constexpr int VEC = 16 / (int)sizeof(T);
+    if (vec) {
+        const int64_t nc = n1 / VEC;
+        const int cnt = (count + VEC - 1) / VEC;
+        int64_t g = wrap1(start / VEC + tid, nc);
+        const int64_t step = NT % nc;
+        for (int i = tid; i < cnt; i += NT) {
+            cp_async<16>(dst + (int64_t)i * VEC, src + g * VEC);
+            g += step;
+            if (g >= nc) g -= nc;
+        }
+    } else {
+        int64_t g = wrap1(start + tid, n1);
+        const int64_t step = NT % n1;
+        for (int i = tid; i < count; i += NT) {
+            cp_async<(int)sizeof(T)>(dst + i, src + g);
+            g += step;
+            if (g >= n1) g -= n1;
+        }
+    }
+}
+
+// shared -> global copy of one tile's band (coalesced 16-byte streaming stores when aligned)
+template <typename T, int NT>
+__device__ __forceinline__ void store_tile(T *band, const T *buf, int64_t t0, int tile, int64_t n1, int tid, bool vec)
+{
+    constexpr int VEC = 16 / (int)sizeof(T);
+    if (vec) {
+        for (int i = tid * VEC; i < tile; i += NT * VEC)
+            if (t0 + i < n1) __stcs(reinterpret_cast<uint4 *>(band + t0 + i), *reinterpret_cast<const uint4 *>(buf + i));
+    } else {
+        for (int i = tid; i < tile; i += NT)
+            if (t0 + i < n1) band[t0 + i] = buf[i];
+    }
+}
+
+// coeffs: [n1][batch][J+1] column-major => band s of signal b starts at (s * batch + b) * n1
+// SPS = output chunks produced together (2 * SPS * VEC independent accumulation chains; the taps are fetched once per
+// group).  Source chunk q of a run lives in ring slot q % NS, NS = WCH + SPS - 1; a group loads the SPS chunks it needs
+// beyond the previous group's window and walks the taps from the oldest source element to the newest, so the loads
+// have the whole group to land.
+template <typename T, int L, int NT, int CPT, int SPS>
+__global__ void __launch_bounds__(NT)
+k_dec1_runs(const T *__restrict__ x, T *__restrict__ coeffs, int64_t n1, int64_t batch, int J, int tile, int wb, int vec,
+            const Taps1<T, L> tp)
+{
+    using C = Casc<T, L>;
+    constexpr int VEC = C::VEC, R = CPT * VEC, WCH = C::WCH_A, NS = WCH + SPS - 1, D = C::HALO_A;
+    extern __shared__ __align__(16) unsigned char smem1_raw[];
+    T *buf0 = reinterpret_cast<T *>(smem1_raw);
+    T *buf1 = buf0 + wb;
+    T *stg0 = buf1 + wb, *stg1 = stg0 + tile;
+    T *dump = stg1 + tile;                             // one chunk: where the detail outputs of halo samples go
+    const int tid = threadIdx.x;
+    const int64_t b = blockIdx.y;
+    const int64_t t0 = (int64_t)blockIdx.x * tile;
+    // level-0 buffer: origin global t0 - J * HLSP
+    stage_wrapped<T, NT>(buf0, x + b * n1, t0 - (int64_t)J * C::HLSP, tile + J * D, n1, tid, vec != 0);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    T *src = buf0, *dst = buf1;
+    for (int j = 1; j <= J; ++j) {
+        const int Wj = tile + (J - j) * D;             // valid outputs of this level
+        const int c0 = (J - j) * C::HLSP;              // buffer index of global t0 at this level (chunk-aligned)
+        T *stg = (j & 1) ? stg1 : stg0;
+        const typename Elem<T>::R thr = tp.thr[j - 1];
+        for (int o = tid * R; o < Wj; o += NT * R) {
+            T w[NS * VEC];
+#pragma unroll
+            for (int q = 0; q < NS; ++q) ld16<T, VEC>(src + o + q * VEC, w + q * VEC);
+#pragma unroll
+            for (int c = 0; c < CPT; c += SPS) {
+                const int n = (CPT - c < SPS) ? CPT - c : SPS;          // compile-time after unrolling
+                if (c > 0) {
+#pragma unroll
+                    for (int q = 0; q < SPS; ++q)
+                        if (q < n) ld16<T, VEC>(src + o + (c + WCH - 1 + q) * VEC, w + ((c + WCH - 1 + q) % NS) * VEC);
+                }
+                T lo[SPS * VEC], hi[SPS * VEC];
+#pragma unroll
+                for (int r = 0; r < SPS * VEC; ++r) { lo[r] = zero_of(T()); hi[r] = zero_of(T()); }
+#pragma unroll
+                for (int k = L - 1; k >= 0; --k)
+#pragma unroll
+                    for (int r = 0; r < SPS * VEC; ++r)
+                        if (r < n * VEC) {
+                            const int idx = c * VEC + r + D - k;        // element of the run's source window
+                            const T e = w[((idx / VEC) % NS) * VEC + idx % VEC];
+                            mac1(lo[r], tp.lo[k], e);
+                            mac1(hi[r], tp.hi[k], e);
+                        }
+                if (thr > 0) {                                          // fused coefficient shrink (uniform per level)
+#pragma unroll
+                    for (int r = 0; r < SPS * VEC; ++r)
+                        if (r < n * VEC) hi[r] = shrink1(hi[r], thr);
+                }
+#pragma unroll
+                for (int q = 0; q < SPS; ++q)
+                    if (q < n) {
+                        st16<T, VEC>(dst + o + (c + q) * VEC, lo + q * VEC);
+                        // detail d_j: only the tile's own samples leave (the others go to the dump chunk, so that the
+                        // lo and hi chains stay interleaved instead of hi being sunk behind a branch)
+                        const int oc = o + (c + q) * VEC - c0;
+                        st16<T, VEC>((oc >= 0 && oc < tile) ? stg + oc : dump, hi + q * VEC);
+                    }
+            }
+        }
+        __syncthreads();
+        // d_j (slot J-j+1) leaves while the next level computes; its staging buffer is rewritten two levels later
+        store_tile<T, NT>(coeffs + ((int64_t)(J - j + 1) * batch + b) * n1, stg, t0, tile, n1, tid, vec != 0);
+        T *t = src; src = dst; dst = t;
+    }
+    store_tile<T, NT>(coeffs + b * n1, src, t0, tile, n1, tid, vec != 0);   // slot 0 = a_J
+}
+
+template <typename T, int L, int NT, int CPT, int SPS>
+__global__ void __launch_bounds__(NT)
+k_rec1_runs(const T *__restrict__ coeffs, T *__restrict__ x, int64_t n1, int64_t batch, int J, int tile, int wb, int vec,
+            const Taps1<T, L> tp)
+{
+    using C = Casc<T, L>;
+    constexpr int VEC = C::VEC, R = CPT * VEC, WCH = C::WCH_R, NS = WCH + SPS - 1, D = C::HALO_R, SR = C::SR;
+    extern __shared__ __align__(16) unsigned char smem1_raw[];
+    T *a0 = reinterpret_cast<T *>(smem1_raw);
+    T *a1 = a0 + wb;
+    T *dd0 = a1 + wb, *dd1 = dd0 + wb;
+    const int tid = threadIdx.x;
+    const int64_t b = blockIdx.y;
+    const int64_t t0 = (int64_t)blockIdx.x * tile;
+    // level-j buffers: origin global t0 - j * HLRP, extent tile + j * D
+    stage_wrapped<T, NT>(a0, coeffs + b * n1, t0 - (int64_t)J * C::HLRP, tile + J * D, n1, tid, vec != 0);
+    stage_wrapped<T, NT>((J & 1) ? dd1 : dd0, coeffs + (batch + b) * n1, t0 - (int64_t)J * C::HLRP, tile + J * D, n1, tid,
+                         vec != 0);
+    cp_async_commit();
+    T *src = a0, *dst = a1;
+    for (int j = J; j >= 1; --j) {
+        // d_{j-1} (slot J-j+2) travels into the other detail buffer while this level computes
+        if (j > 1)
+            stage_wrapped<T, NT>(((j - 1) & 1) ? dd1 : dd0, coeffs + ((int64_t)(J - j + 2) * batch + b) * n1,
+                                 t0 - (int64_t)(j - 1) * C::HLRP, tile + (j - 1) * D, n1, tid, vec != 0);
+        cp_async_commit();
+        cp_async_wait<1>();                            // everything but the group just committed has landed
+        __syncthreads();
+        const T *dj = (j & 1) ? dd1 : dd0;
+        const int Wo = tile + (j - 1) * D;             // outputs a_{j-1}
+        for (int o = tid * R; o < Wo; o += NT * R) {
+            T wa[NS * VEC], wd[NS * VEC];
+#pragma unroll
+            for (int q = 0; q < NS; ++q) {
+                ld16<T, VEC>(src + o + q * VEC, wa + q * VEC);
+                ld16<T, VEC>(dj + o + q * VEC, wd + q * VEC);
+            }
+#pragma unroll
+            for (int c = 0; c < CPT; c += SPS) {
+                const int n = (CPT - c < SPS) ? CPT - c : SPS;
+                if (c > 0) {
+#pragma unroll
+                    for (int q = 0; q < SPS; ++q)
+                        if (q < n) {
+                            ld16<T, VEC>(src + o + (c + WCH - 1 + q) * VEC, wa + ((c + WCH - 1 + q) % NS) * VEC);
+                            ld16<T, VEC>(dj + o + (c + WCH - 1 + q) * VEC, wd + ((c + WCH - 1 + q) % NS) * VEC);
+                        }
+                }
+                T acc[SPS * VEC], acd[SPS * VEC];
+#pragma unroll
+                for (int r = 0; r < SPS * VEC; ++r) { acc[r] = zero_of(T()); acd[r] = zero_of(T()); }
+#pragma unroll
+                for (int k = 0; k < L; ++k)            // ascending taps = oldest source element first
+#pragma unroll
+                    for (int r = 0; r < SPS * VEC; ++r)
+                        if (r < n * VEC) {
+                            const int idx = c * VEC + r + SR + k;
+                            mac1(acc[r], tp.lo[k], wa[((idx / VEC) % NS) * VEC + idx % VEC]);
+                            mac1(acd[r], tp.hi[k], wd[((idx / VEC) % NS) * VEC + idx % VEC]);
+                        }
+#pragma unroll
+                for (int r = 0; r < SPS * VEC; ++r)
+                    if (r < n * VEC) acc[r] = add(acc[r], acd[r]);
+#pragma unroll
+                for (int q = 0; q < SPS; ++q)
+                    if (q < n) st16<T, VEC>(dst + o + (c + q) * VEC, acc + q * VEC);
+            }
+        }
+        __syncthreads();
+        T *t = src; src = dst; dst = t;
+    }
+    store_tile<T, NT>(x + b * n1, src, t0, tile, n1, tid, vec != 0);
+}
+
 template <typename T, int L>
 static Taps1<T, L> make_taps1(const nddwt_plan *p, bool rec)
 {
@@ -195,10 +429,19 @@ static Taps1<T, L> make_taps1(const nddwt_plan *p, bool rec)
     return t;
 }
 
-template <typename T, int L, int TILE>
-static int launch1(nddwt_plan *p, bool rec, const void *in, void *out, int J, cudaStream_t s)
+#ifdef NDDWT_TUNING
+static int tuning1_env(const char *name, int dflt)
 {
-    constexpr int NT = 256, CPT = 1;   // 16-byte chunks per thread and level (2: measured slower, 7.1 + 10.4 ms vs 5.4 + 9.6 ms on cfg2)
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+#endif
+
+// first-version launch (tuning builds only: the A/B partner of the run kernels)
+template <typename T, int L, int TILE>
+static int launch1_v1(nddwt_plan *p, bool rec, const void *in, void *out, int J, cudaStream_t s)
+{
+    constexpr int NT = 256, CPT = 1;
     const int64_t n1 = p->dims[0], batch = p->batch;
     const size_t W = ((size_t)TILE + (size_t)J * (L - 1) + 4 * (16 / sizeof(T)) + 3) & ~(size_t)3;
     const size_t smem = (rec ? 3 : 2) * W * sizeof(T);
@@ -222,11 +465,67 @@ static int launch1(nddwt_plan *p, bool rec, const void *in, void *out, int J, cu
     return 0;
 }
 
+// run kernels: NT threads, runs of CPT chunks; the tile is sized so that the widest level of the cascade is
+// exactly `kit` iterations of the CTA
+template <typename T, int L, int NT, int CPT, int SPS = 2>
+static int launch1_runs(nddwt_plan *p, bool rec, const void *in, void *out, int J, cudaStream_t s)
+{
+    using C = Casc<T, L>;
+    constexpr int VEC = C::VEC, R = CPT * VEC;
+    static_assert(CPT % 2 == 1, "odd chunk stride between lanes: conflict-free 16-byte shared-memory accesses");
+    const int64_t n1 = p->dims[0], batch = p->batch;
+    const int halo = rec ? C::HALO_R : C::HALO_A, wch = rec ? C::WCH_R : C::WCH_A;
+    const int64_t grow = (int64_t)(J - 1) * halo;          // the widest level computes tile + grow outputs
+    int kit = 1;
+    while (kit < 8 && (int64_t)kit * NT * R - grow < 2 * grow + VEC) ++kit;
+    int64_t tile = ((int64_t)kit * NT * R - grow) / VEC * VEC;
+    if (tile < VEC) return 1;
+    const int64_t n1r = (n1 + VEC - 1) / VEC * VEC;
+    if (tile > n1r) tile = n1r;
+    // buffers: a level's extent + what the last run may touch beyond it (its outputs, its window, the chunk ahead)
+    const int64_t wb = (tile + (int64_t)J * halo + R + (int64_t)(wch + SPS + 1) * VEC + VEC - 1) / VEC * VEC;
+    const size_t smem = (size_t)(rec ? 4 * wb : 2 * wb + 2 * tile + VEC) * sizeof(T);
+    if (smem > 200 * 1024 || batch > 65535 || (n1 + tile - 1) / tile > 0x7fffffff) return 1;
+    const int vec = (n1 % VEC == 0 && (uintptr_t)in % 16 == 0 && (uintptr_t)out % 16 == 0) ? 1 : 0;
+    dim3 grid((unsigned)((n1 + tile - 1) / tile), (unsigned)batch);
+    if (rec) {
+        auto kern = k_rec1_runs<T, L, NT, CPT, SPS>;
+        NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LaunchTimer lt(p, KIND_REC3, s);
+        kern<<<grid, NT, smem, s>>>(reinterpret_cast<const T *>(in), reinterpret_cast<T *>(out), n1, batch, J, (int)tile,
+                                    (int)wb, vec, make_taps1<T, L>(p, true));
+    } else {
+        auto kern = k_dec1_runs<T, L, NT, CPT, SPS>;
+        NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LaunchTimer lt(p, KIND_DEC3, s);
+        kern<<<grid, NT, smem, s>>>(reinterpret_cast<const T *>(in), reinterpret_cast<T *>(out), n1, batch, J, (int)tile,
+                                    (int)wb, vec, make_taps1<T, L>(p, false));
+    }
+    p->launches++;
+    NDDWT_CUDA(cudaGetLastError());
+    return 0;
+}
+
 template <typename T, int L>
 static int launch1_tile(nddwt_plan *p, bool rec, const void *in, void *out, int J, cudaStream_t s)
 {
-    if (p->dims[0] >= 1024) return launch1<T, L, 2048>(p, rec, in, out, J, s);
-    return launch1<T, L, 256>(p, rec, in, out, J, s);
+#ifdef NDDWT_TUNING
+    if constexpr (L == 16 && sizeof(T) == 8 && Elem<T>::cplx) {
+        switch (tuning1_env("NDDWT_CASC", 0)) {
+            case 1:
+                if (p->dims[0] >= 1024) return launch1_v1<T, L, 2048>(p, rec, in, out, J, s);
+                return launch1_v1<T, L, 256>(p, rec, in, out, J, s);
+            case 2: return launch1_runs<T, L, 128, 7, 1>(p, rec, in, out, J, s);   // one chunk at a time (2 VEC chains)
+            case 3: return launch1_runs<T, L, 128, 7, 4>(p, rec, in, out, J, s);
+            case 4: return launch1_runs<T, L, 128, 9, 3>(p, rec, in, out, J, s);
+            case 5: return launch1_runs<T, L, 128, 5, 2>(p, rec, in, out, J, s);
+            case 6: return launch1_runs<T, L, 256, 7, 2>(p, rec, in, out, J, s);
+            case 7: return launch1_runs<T, L, 128, 11, 2>(p, rec, in, out, J, s);
+            default: break;
+        }
+    }
+#endif
+    return launch1_runs<T, L, 128, 7>(p, rec, in, out, J, s);
 }
 
 #define NDDWT1_L_SWITCH(L_, CALL)                          \
