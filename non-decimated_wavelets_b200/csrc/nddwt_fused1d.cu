@@ -11,12 +11,6 @@
 
 namespace nddwt {
 
-__device__ __forceinline__ int64_t wrap1(int64_t m, int64_t n)
-{
-    m %= n;
-    return m < 0 ? m + n : m;
-}
-
 // complex single: taps duplicated (t, t) so that one FFMA2 updates (re, im)
 template <typename T> struct Tap1Of { using type = typename Elem<T>::R; };
 template <> struct Tap1Of<float2> { using type = float2; };
@@ -35,20 +29,6 @@ struct Taps1 {
     typename Elem<T>::R thr[NDDWT_MAX_LEVELS];   // fused coefficient shrink: soft threshold of d_j (0 = keep), analysis only
 };
 
-// contiguous periodic copy global -> shared: one wrap computation per thread, then increments
-template <typename T, int NT>
-__device__ __forceinline__ void load_wrapped(T *dst, const T *src, int64_t start, int count, int64_t n1, int tid)
-{
-    int64_t g = wrap1(start + tid, n1);
-    const int64_t step = NT % n1;
-    for (int i = tid; i < count; i += NT) {
-        dst[i] = __ldg(src + g);
-        g += step;
-        if (g >= n1) g -= n1;
-    }
-}
-
-
 template <typename T, int VEC>
 __device__ __forceinline__ void ld16(const T *p, T *dst)
 {
@@ -66,136 +46,24 @@ __device__ __forceinline__ void st16(T *p, const T *src)
     *reinterpret_cast<uint4 *>(p) = cv.u;
 }
 
-// coeffs: [n1][batch][J+1] column-major => band s of signal b starts at (s * batch + b) * n1
-template <typename T, int L, int TILE, int NT, int CPT>
-__global__ void __launch_bounds__(NT)
-k_dec1_cascade(const T *__restrict__ x, T *__restrict__ coeffs, int64_t n1, int64_t batch, int J,
-               const Taps1<T, L> tp)
-{
-    constexpr int HLs = L / 2 - 1;                 // analysis reads n-(L/2-1) .. n+L/2
-    extern __shared__ __align__(16) unsigned char smem1_raw[];
-    const int W0 = (TILE + J * (L - 1) + 4 * (16 / (int)sizeof(T)) + 3) & ~3;   // slack for whole-chunk accesses
-    T *buf0 = reinterpret_cast<T *>(smem1_raw);
-    T *buf1 = buf0 + W0;
-    const int tid = threadIdx.x;
-    const int64_t b = blockIdx.y;
-    const int64_t t0 = (int64_t)blockIdx.x * TILE;
-    const T *xs = x + b * n1;
-    // level-0 buffer: origin global t0 - J*(L/2-1)
-    load_wrapped<T, NT>(buf0, xs, t0 - (int64_t)J * HLs, TILE + J * (L - 1), n1, tid);
-    __syncthreads();
-    T *src = buf0, *dst = buf1;
-    for (int j = 1; j <= J; ++j) {
-        const int Wj = TILE + (J - j) * (L - 1);       // valid outputs of this level
-        const int c0 = (J - j) * HLs;                   // buffer index of global t0 at this level
-        T *band = coeffs + ((int64_t)(J - j + 1) * batch + b) * n1;     // detail d_j lives in slot J-j+1
-        // each thread produces CPT 16-byte chunks (R consecutive outputs) from NCH chunk loads; the tap loop is
-        // outermost so that the 2 R accumulations are independent FFMA2 chains (two chains per thread stall on
-        // the FFMA2 latency: profiles/r01_rows_kernel.md)
-        constexpr int VEC = 16 / (int)sizeof(T), R = CPT * VEC, NCH = (R + L - 1 + VEC - 1) / VEC;
-        for (int o = tid * R; o < Wj; o += NT * R) {
-            T v[NCH * VEC];
-#pragma unroll
-            for (int q = 0; q < NCH; ++q) ld16<T, VEC>(src + o + q * VEC, v + q * VEC);
-            T lo[R], hi[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) { lo[r] = zero_of(T()); hi[r] = zero_of(T()); }
-#pragma unroll
-            for (int k = 0; k < L; ++k)
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    mac1(lo[r], tp.lo[k], v[r + (L - 1) - k]);
-                    mac1(hi[r], tp.hi[k], v[r + (L - 1) - k]);
-                }
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) st16<T, VEC>(dst + o + c * VEC, lo + c * VEC);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int64_t g = t0 + (o + r - c0);
-                if (o + r >= c0 && o + r < c0 + TILE && g < n1) band[g] = shrink1(hi[r], tp.thr[j - 1]);
-            }
-        }
-        __syncthreads();
-        T *t = src; src = dst; dst = t;
-    }
-    T *approx = coeffs + b * n1;                        // slot 0 = a_J
-    for (int o = tid; o < TILE; o += NT)
-        if (t0 + o < n1) approx[t0 + o] = src[o];
-}
-
-template <typename T, int L, int TILE, int NT, int CPT>
-__global__ void __launch_bounds__(NT)
-k_rec1_cascade(const T *__restrict__ coeffs, T *__restrict__ x, int64_t n1, int64_t batch, int J,
-               const Taps1<T, L> tp)
-{
-    constexpr int HLr = L / 2;                     // synthesis reads n-L/2 .. n+L/2-1
-    extern __shared__ __align__(16) unsigned char smem1_raw[];
-    const int WJ = (TILE + J * (L - 1) + 4 * (16 / (int)sizeof(T)) + 3) & ~3;
-    T *a0 = reinterpret_cast<T *>(smem1_raw);
-    T *a1 = a0 + WJ;
-    T *dd = a1 + WJ;
-    const int tid = threadIdx.x;
-    const int64_t b = blockIdx.y;
-    const int64_t t0 = (int64_t)blockIdx.x * TILE;
-    // a_J on [t0 - J*L/2, t0 + TILE + J*(L/2-1))
-    {
-        const T *aJ = coeffs + b * n1;
-        load_wrapped<T, NT>(a0, aJ, t0 - (int64_t)J * HLr, TILE + J * (L - 1), n1, tid);
-    }
-    T *src = a0, *dst = a1;
-    for (int j = J; j >= 1; --j) {
-        const int Wj = TILE + j * (L - 1);             // extent of a_j / d_j needed at this level
-        const T *dj = coeffs + ((int64_t)(J - j + 1) * batch + b) * n1;
-        load_wrapped<T, NT>(dd, dj, t0 - (int64_t)j * HLr, Wj, n1, tid);
-        __syncthreads();
-        const int Wo = Wj - (L - 1);                   // outputs a_{j-1}
-        constexpr int VEC = 16 / (int)sizeof(T), R = CPT * VEC, NCH = (R + L - 1 + VEC - 1) / VEC;
-        for (int o = tid * R; o < Wo; o += NT * R) {
-            T va[NCH * VEC], vd[NCH * VEC];
-#pragma unroll
-            for (int q = 0; q < NCH; ++q) {
-                ld16<T, VEC>(src + o + q * VEC, va + q * VEC);
-                ld16<T, VEC>(dd + o + q * VEC, vd + q * VEC);
-            }
-            // approximation and detail parts in separate accumulators, tap loop outermost: 2 R independent chains
-            T acc[R], acd[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) { acc[r] = zero_of(T()); acd[r] = zero_of(T()); }
-#pragma unroll
-            for (int k = 0; k < L; ++k)
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    mac1(acc[r], tp.lo[k], va[r + k]);
-                    mac1(acd[r], tp.hi[k], vd[r + k]);
-                }
-#pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = add(acc[r], acd[r]);
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) st16<T, VEC>(dst + o + c * VEC, acc + c * VEC);
-        }
-        __syncthreads();
-        T *t = src; src = dst; dst = t;
-    }
-    T *xs = x + b * n1;
-    for (int o = tid; o < TILE; o += NT)
-        if (t0 + o < n1) xs[t0 + o] = src[o];
-}
-
-
-// =============================================================================================
-// Round-2 cascade kernels ("runs"): the same one-launch J-level scheme, rebuilt around the two things that bound
-// the first version on BASELINE configs[1] (4096 x 65536, db8, J6, complex single: 5.5 + 8.9 ms against an FP32
-// floor of 2.9 + 2.9 ms): shared-memory wavefronts (9 / 18 16-byte loads per 2 outputs) and idle threads (a 2048 +
-// halo tile is 4.2 iterations of 256 threads x 2 outputs, i.e. 5).
-//   * a thread produces a RUN of R = CPT x VEC consecutive outputs per level with a sliding window of the
-//     source held in a static register ring (one 16-byte load per VEC outputs, the next chunk one step ahead);
-//     CPT is odd, so the lanes' 16-byte accesses (stride CPT chunks) are bank-conflict-free;
+// ---------------------------------------------------------------------------------------------
+// Run kernels (round 2).  The first version of the cascade (256 threads, 2 outputs per thread and iteration,
+// 2048-sample tiles) took 5.5 + 8.9 ms on BASELINE configs[1] (4096 x 65536, db8, J6, complex single) against an
+// FP32-issue floor of 2.9 + 2.9 ms: 9 / 18 16-byte shared-memory loads per 2 outputs, a tile of 2048 + halo
+// samples = 4.2 iterations of the CTA (i.e. 5), element-wise detail stores, a 64-bit modulo per level and thread.
+//   * a thread produces a RUN of R = CPT x VEC consecutive outputs per level from a sliding window of the source
+//     held in a statically indexed register ring (one 16-byte load per VEC outputs); CPT is odd, so the lanes'
+//     16-byte accesses (stride CPT chunks) are bank-conflict-free;
 //   * the tile length is chosen on the host so that the widest level is exactly `kit` full iterations of the CTA;
 //   * every level's buffer origin moves by the halo rounded up to whole 16-byte chunks (the window then starts
-//     SA / SR elements into its first chunk), so that shared and global accesses stay chunk-aligned at every level;
+//     SA / SR elements into its first chunk), so shared and global accesses stay chunk-aligned at every level;
 //   * analysis: the detail outputs of a level are staged in shared memory (double-buffered) and leave as coalesced
 //     16-byte streaming stores while the next level computes;  synthesis: d_{j-1} is fetched by cp.async into the
-//     other detail buffer while level j computes (no exposed global latency per level).
+//     other detail buffer while level j computes (no exposed global latency per level);
+//   * the soft threshold runs only on levels whose threshold is non-zero.
+// Measured steps (cfg2, ms per launch, analysis + synthesis): 5.58 + 8.94 -> 5.38 + 4.85 (runs) -> 4.57 + 5.02
+// (threshold skipped, lo / hi chains interleaved) -> 4.32 + 4.47 (no integer division in the staging loops, leaner
+// store loops): pair 14.45 -> 8.8 ms, 36 % -> 60 % of the HBM roofline of the pair (profiles/r02_variants.md).
 template <typename T, int L>
 struct Casc {
     static constexpr int VEC = 16 / (int)sizeof(T);
@@ -221,23 +89,25 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // asynchronous periodic copy global -> shared of `count` elements starting at global index `start` (any sign).
 // vec: start and n1 are multiples of VEC and src is 16-byte aligned -> whole chunks, none straddles the wrap.
+// Index arithmetic without integer division on the usual path (a 64-bit modulo is ~100 instructions and this runs once
+// per level in the synthesis cascade: 22 % of the stall samples of the first version, profiles/r02_cfg2_ncu.txt).
 template <typename T, int NT>
 __device__ __forceinline__ void stage_wrapped(T *dst, const T *src, int64_t start, int count, int64_t n1, int tid, bool vec)
 {
     constexpr int VEC = 16 / (int)sizeof(T);
     if (vec) {
-        const int64_t nc = n1 / VEC;
+        const int64_t nc = n1 / VEC;                    // (a shift: VEC is a power of two and n1 >= 0)
         const int cnt = (count + VEC - 1) / VEC;
-        int64_t g = wrap1(start / VEC + tid, nc);
-        const int64_t step = NT % nc;
+        int64_t g = wrap(start / VEC + tid, nc);
+        const int64_t step = (NT < nc) ? NT : NT % nc;
         for (int i = tid; i < cnt; i += NT) {
             cp_async<16>(dst + (int64_t)i * VEC, src + g * VEC);
             g += step;
             if (g >= nc) g -= nc;
         }
     } else {
-        int64_t g = wrap1(start + tid, n1);
-        const int64_t step = NT % n1;
+        int64_t g = wrap(start + tid, n1);
+        const int64_t step = (NT < n1) ? NT : NT % n1;
         for (int i = tid; i < count; i += NT) {
             cp_async<(int)sizeof(T)>(dst + i, src + g);
             g += step;
@@ -246,17 +116,21 @@ __device__ __forceinline__ void stage_wrapped(T *dst, const T *src, int64_t star
     }
 }
 
-// shared -> global copy of one tile's band (coalesced 16-byte streaming stores when aligned)
+// shared -> global copy of one tile's band (coalesced 16-byte streaming stores when aligned); `lim` = samples of the
+// tile inside the signal (a multiple of VEC when vec)
 template <typename T, int NT>
-__device__ __forceinline__ void store_tile(T *band, const T *buf, int64_t t0, int tile, int64_t n1, int tid, bool vec)
+__device__ __forceinline__ void store_tile(T *__restrict__ band_tile, const T *__restrict__ buf, int lim, int tid, bool vec)
 {
     constexpr int VEC = 16 / (int)sizeof(T);
     if (vec) {
-        for (int i = tid * VEC; i < tile; i += NT * VEC)
-            if (t0 + i < n1) __stcs(reinterpret_cast<uint4 *>(band + t0 + i), *reinterpret_cast<const uint4 *>(buf + i));
+        uint4 *g = reinterpret_cast<uint4 *>(band_tile);
+        const uint4 *sm = reinterpret_cast<const uint4 *>(buf);
+        const int nch = lim / VEC;
+#pragma unroll 4
+        for (int i = tid; i < nch; i += NT) __stcs(g + i, sm[i]);
     } else {
-        for (int i = tid; i < tile; i += NT)
-            if (t0 + i < n1) band[t0 + i] = buf[i];
+#pragma unroll 4
+        for (int i = tid; i < lim; i += NT) band_tile[i] = buf[i];
     }
 }
 
@@ -280,6 +154,7 @@ k_dec1_runs(const T *__restrict__ x, T *__restrict__ coeffs, int64_t n1, int64_t
     const int tid = threadIdx.x;
     const int64_t b = blockIdx.y;
     const int64_t t0 = (int64_t)blockIdx.x * tile;
+    const int lim = (int)((n1 - t0 < tile) ? n1 - t0 : tile);   // samples of this tile inside the signal
     // level-0 buffer: origin global t0 - J * HLSP
     stage_wrapped<T, NT>(buf0, x + b * n1, t0 - (int64_t)J * C::HLSP, tile + J * D, n1, tid, vec != 0);
     cp_async_commit();
@@ -334,10 +209,10 @@ k_dec1_runs(const T *__restrict__ x, T *__restrict__ coeffs, int64_t n1, int64_t
         }
         __syncthreads();
         // d_j (slot J-j+1) leaves while the next level computes; its staging buffer is rewritten two levels later
-        store_tile<T, NT>(coeffs + ((int64_t)(J - j + 1) * batch + b) * n1, stg, t0, tile, n1, tid, vec != 0);
+        store_tile<T, NT>(coeffs + ((int64_t)(J - j + 1) * batch + b) * n1 + t0, stg, lim, tid, vec != 0);
         T *t = src; src = dst; dst = t;
     }
-    store_tile<T, NT>(coeffs + b * n1, src, t0, tile, n1, tid, vec != 0);   // slot 0 = a_J
+    store_tile<T, NT>(coeffs + b * n1 + t0, src, lim, tid, vec != 0);   // slot 0 = a_J
 }
 
 template <typename T, int L, int NT, int CPT, int SPS>
@@ -411,7 +286,7 @@ k_rec1_runs(const T *__restrict__ coeffs, T *__restrict__ x, int64_t n1, int64_t
         __syncthreads();
         T *t = src; src = dst; dst = t;
     }
-    store_tile<T, NT>(x + b * n1, src, t0, tile, n1, tid, vec != 0);
+    store_tile<T, NT>(x + b * n1 + t0, src, (int)((n1 - t0 < tile) ? n1 - t0 : tile), tid, vec != 0);
 }
 
 template <typename T, int L>
@@ -437,37 +312,9 @@ static int tuning1_env(const char *name, int dflt)
 }
 #endif
 
-// first-version launch (tuning builds only: the A/B partner of the run kernels)
-template <typename T, int L, int TILE>
-static int launch1_v1(nddwt_plan *p, bool rec, const void *in, void *out, int J, cudaStream_t s)
-{
-    constexpr int NT = 256, CPT = 1;
-    const int64_t n1 = p->dims[0], batch = p->batch;
-    const size_t W = ((size_t)TILE + (size_t)J * (L - 1) + 4 * (16 / sizeof(T)) + 3) & ~(size_t)3;
-    const size_t smem = (rec ? 3 : 2) * W * sizeof(T);
-    if (smem > 200 * 1024 || batch > 65535) return 1;
-    dim3 grid((unsigned)((n1 + TILE - 1) / TILE), (unsigned)batch);
-    if (rec) {
-        auto kern = k_rec1_cascade<T, L, TILE, NT, CPT>;
-        NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LaunchTimer lt(p, KIND_REC3, s);
-        kern<<<grid, NT, smem, s>>>(reinterpret_cast<const T *>(in), reinterpret_cast<T *>(out), n1, batch, J,
-                                    make_taps1<T, L>(p, true));
-    } else {
-        auto kern = k_dec1_cascade<T, L, TILE, NT, CPT>;
-        NDDWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LaunchTimer lt(p, KIND_DEC3, s);
-        kern<<<grid, NT, smem, s>>>(reinterpret_cast<const T *>(in), reinterpret_cast<T *>(out), n1, batch, J,
-                                    make_taps1<T, L>(p, false));
-    }
-    p->launches++;
-    NDDWT_CUDA(cudaGetLastError());
-    return 0;
-}
-
 // run kernels: NT threads, runs of CPT chunks; the tile is sized so that the widest level of the cascade is
 // exactly `kit` iterations of the CTA
-template <typename T, int L, int NT, int CPT, int SPS = 2>
+template <typename T, int L, int NT, int CPT, int SPS>
 static int launch1_runs(nddwt_plan *p, bool rec, const void *in, void *out, int J, cudaStream_t s)
 {
     using C = Casc<T, L>;
@@ -512,20 +359,15 @@ static int launch1_tile(nddwt_plan *p, bool rec, const void *in, void *out, int 
 #ifdef NDDWT_TUNING
     if constexpr (L == 16 && sizeof(T) == 8 && Elem<T>::cplx) {
         switch (tuning1_env("NDDWT_CASC", 0)) {
-            case 1:
-                if (p->dims[0] >= 1024) return launch1_v1<T, L, 2048>(p, rec, in, out, J, s);
-                return launch1_v1<T, L, 256>(p, rec, in, out, J, s);
-            case 2: return launch1_runs<T, L, 128, 7, 1>(p, rec, in, out, J, s);   // one chunk at a time (2 VEC chains)
-            case 3: return launch1_runs<T, L, 128, 7, 4>(p, rec, in, out, J, s);
-            case 4: return launch1_runs<T, L, 128, 9, 3>(p, rec, in, out, J, s);
-            case 5: return launch1_runs<T, L, 128, 5, 2>(p, rec, in, out, J, s);
-            case 6: return launch1_runs<T, L, 256, 7, 2>(p, rec, in, out, J, s);
-            case 7: return launch1_runs<T, L, 128, 11, 2>(p, rec, in, out, J, s);
+            case 2: return launch1_runs<T, L, 128, 7, 2>(p, rec, in, out, J, s);   // two chunks per group: 4.33 + 4.56 ms (cfg2)
+            case 5: return launch1_runs<T, L, 128, 5, 2>(p, rec, in, out, J, s);   // 5 CTAs per SM: 4.35 + 4.88 ms
             default: break;
         }
     }
 #endif
-    return launch1_runs<T, L, 128, 7>(p, rec, in, out, J, s);
+    // 128 threads x runs of 7 chunks, one chunk per group: 4.32 + 4.47 ms on cfg2 (256 threads: 4.9 + 6.0; runs of 9 / 11
+    // chunks, groups of 3 / 4 chunks: within 5 %, profiles/r02_variants.md)
+    return launch1_runs<T, L, 128, 7, 1>(p, rec, in, out, J, s);
 }
 
 #define NDDWT1_L_SWITCH(L_, CALL)                          \

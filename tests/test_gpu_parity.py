@@ -367,7 +367,7 @@ def test_4d_full_size_properties_cfg5():
     assert float(torch.linalg.vector_norm(yab)) / float(torch.linalg.vector_norm(yb)) <= 1e-5   # linearity
 
 
-@pytest.mark.parametrize("sizes,wn,level,batch", [((4096,), "db8", 6, 8), ((64, 48), ["db2", "db3"], 2, 5),
+@pytest.mark.parametrize("sizes,wn,level,batch", [((4096,), "db8", 6, 8), ((1001,), "db5", 4, 3), ((64, 48), ["db2", "db3"], 2, 5),
                                                     ((32, 24, 16), "db4", 2, 3)])
 def test_batched_extension(sizes, wn, level, batch):
     """Batch API (extension): x is [sizes, B]; every slice equals the un-batched transform."""
@@ -382,8 +382,9 @@ def test_batched_extension(sizes, wn, level, batch):
     assert orc.rel_l2(o.rec(y), x) <= 1e-5
 
 
-@pytest.mark.parametrize("n,wn,level", [(54321, "db1", 4), (4099, "db8", 6), (300, "db10", 3), (61, "db3", 5), (65536, "db4", 8)])
-@pytest.mark.parametrize("dtype", ["complex64", "float64"])
+@pytest.mark.parametrize("n,wn,level", [(54321, "db1", 4), (4099, "db8", 6), (300, "db10", 3), (61, "db3", 5), (65536, "db4", 8),
+                                        (16, "db8", 3), (18, "db7", 2), (7000, "db2", 5), (2, "db1", 3), (3586, "db8", 6), (12288, "db6", 1)])
+@pytest.mark.parametrize("dtype", ["complex64", "float64", "float32", "complex128"])
 def test_fused_1d_cascade(n, wn, level, dtype):
     """1-D cascade kernel (all levels in one launch) == generic per-level kernels == oracle."""
     prec = _prec(dtype)
