@@ -78,26 +78,57 @@ struct Casc {
 };
 
 template <int B>
+__device__ __forceinline__ void cp_async_sa(unsigned smem_addr, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr), "l"(__cvta_generic_to_global(gmem)), "n"(B) : "memory");
+}
+template <int B>
 __device__ __forceinline__ void cp_async(void *smem, const void *gmem)
 {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(sa), "l"(__cvta_generic_to_global(gmem)), "n"(B) : "memory");
+    cp_async_sa<B>((unsigned)__cvta_generic_to_shared(smem), gmem);
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// `cnt` pieces of B bytes, piece i of thread tid at byte offset (tid + i NT) B of both sides: constant strides, so the
+// unrolled body is one LDGSTS per piece with immediate offsets
+template <int B, int NT>
+__device__ __forceinline__ void stage_linear(void *dst, const void *src, int cnt, int tid)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(dst) + (unsigned)tid * B;
+    const char *g = reinterpret_cast<const char *>(src) + (size_t)tid * B;
+    int i = tid;
+    for (; i + 3 * NT < cnt; i += 4 * NT) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cp_async_sa<B>(sa + u * NT * B, g + u * NT * B);
+        sa += 4 * NT * B;
+        g += 4 * NT * B;
+    }
+    for (; i < cnt; i += NT) {
+        cp_async_sa<B>(sa, g);
+        sa += NT * B;
+        g += NT * B;
+    }
+}
+
 // asynchronous periodic copy global -> shared of `count` elements starting at global index `start` (any sign).
 // vec: start and n1 are multiples of VEC and src is 16-byte aligned -> whole chunks, none straddles the wrap.
-// Index arithmetic without integer division on the usual path (a 64-bit modulo is ~100 instructions and this runs once
-// per level in the synthesis cascade: 22 % of the stall samples of the first version, profiles/r02_cfg2_ncu.txt).
+// All but the first / last tiles of a signal take the linear path (the window lies inside the signal); the periodic
+// path runs without integer division unless the window is longer than the signal (a 64-bit modulo is ~100
+// instructions and this runs once per level in the synthesis cascade: 22 % of the stall samples of the first run-kernel
+// form; the per-piece wrap bookkeeping was still 28 % of the instructions of the second, profiles/r02_cfg2_ncu.txt).
 template <typename T, int NT>
 __device__ __forceinline__ void stage_wrapped(T *dst, const T *src, int64_t start, int count, int64_t n1, int tid, bool vec)
 {
     constexpr int VEC = 16 / (int)sizeof(T);
     if (vec) {
-        const int64_t nc = n1 / VEC;                    // (a shift: VEC is a power of two and n1 >= 0)
         const int cnt = (count + VEC - 1) / VEC;
+        if (start >= 0 && start + (int64_t)cnt * VEC <= n1) {
+            stage_linear<16, NT>(dst, src + start, cnt, tid);
+            return;
+        }
+        const int64_t nc = n1 / VEC;                    // (a shift: VEC is a power of two and n1 >= 0)
         int64_t g = wrap(start / VEC + tid, nc);
         const int64_t step = (NT < nc) ? NT : NT % nc;
         for (int i = tid; i < cnt; i += NT) {
@@ -106,6 +137,10 @@ __device__ __forceinline__ void stage_wrapped(T *dst, const T *src, int64_t star
             if (g >= nc) g -= nc;
         }
     } else {
+        if (start >= 0 && start + count <= n1) {
+            stage_linear<(int)sizeof(T), NT>(dst, src + start, count, tid);
+            return;
+        }
         int64_t g = wrap(start + tid, n1);
         const int64_t step = (NT < n1) ? NT : NT % n1;
         for (int i = tid; i < count; i += NT) {
@@ -117,17 +152,30 @@ __device__ __forceinline__ void stage_wrapped(T *dst, const T *src, int64_t star
 }
 
 // shared -> global copy of one tile's band (coalesced 16-byte streaming stores when aligned); `lim` = samples of the
-// tile inside the signal (a multiple of VEC when vec)
+// tile inside the signal (a multiple of VEC when vec).  Constant strides: one LDS + one STG per piece when unrolled.
 template <typename T, int NT>
 __device__ __forceinline__ void store_tile(T *__restrict__ band_tile, const T *__restrict__ buf, int lim, int tid, bool vec)
 {
     constexpr int VEC = 16 / (int)sizeof(T);
     if (vec) {
-        uint4 *g = reinterpret_cast<uint4 *>(band_tile);
-        const uint4 *sm = reinterpret_cast<const uint4 *>(buf);
+        uint4 *g = reinterpret_cast<uint4 *>(band_tile) + tid;
+        const uint4 *sm = reinterpret_cast<const uint4 *>(buf) + tid;
         const int nch = lim / VEC;
-#pragma unroll 4
-        for (int i = tid; i < nch; i += NT) __stcs(g + i, sm[i]);
+        int i = tid;
+        for (; i + 3 * NT < nch; i += 4 * NT) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = sm[u * NT];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) __stcs(g + u * NT, v[u]);
+            sm += 4 * NT;
+            g += 4 * NT;
+        }
+        for (; i < nch; i += NT) {
+            __stcs(g, *sm);
+            sm += NT;
+            g += NT;
+        }
     } else {
 #pragma unroll 4
         for (int i = tid; i < lim; i += NT) band_tile[i] = buf[i];
