@@ -193,6 +193,30 @@ def test_device_resident_path_and_input_not_mutated():
     assert torch.equal(xd, nd.to_device(x))
 
 
+@pytest.mark.parametrize("sizes,wn,level", [((256, 256), "db4", 3), ((4096,), "db8", 4), ((64, 48, 40), "db4", 2), ((32, 32, 24, 16), "db4", 2)])
+def test_cuda_graph_capture_and_replay(sizes, wn, level):
+    """Once a plan's scratch exists, dec and rec only launch kernels on the caller's stream (no allocation, no
+    synchronisation, no host round trip), so the dec/rec pair of an iterative loop can be captured into a CUDA graph and
+    replayed on new data -- what a launch-bound small problem (BASELINE configs[0], 256 x 256) wants."""
+    import torch
+    x1 = orc.synth(sizes, np.complex64, 77)
+    x2 = orc.synth(sizes, np.complex64, 78)
+    o = CLS[len(sizes)](wn, list(sizes), "precision", "single", "compute", "gpu")
+    xd = nd.to_device(x1)
+    o.rec(o.dec(xd, level))                      # warm-up outside the capture: plan scratch gets allocated here
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        yd = o.dec(xd, level)
+        xr = o.rec(yd)
+    xd.copy_(nd.to_device(x2))                   # new input in the captured buffer
+    g.replay()
+    g.replay()
+    torch.cuda.synchronize()
+    assert orc.rel_l2(nd.to_host(yd), orc.dec_direct(x2.astype(np.complex128), wn, level)) <= 1e-5
+    assert orc.rel_l2(nd.to_host(xr), x2) <= 1e-5
+
+
 def test_nd_dwt_mex_entry():
     x = orc.synth((32, 20), np.complex128, 1)
     f = nd.FilterSpec(["db2", "db3"], [32, 20])

@@ -4,7 +4,7 @@
 PV=${1:-"0"}; BV=${2:-"0"}
 for v in $PV; do
   echo "== parity NDDWT_CASC=$v"
-  NDDWT_CASC=$v timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_shrink.py -m gpu -x -q -k "1d or cfg2 or batched or golden or parity_vs_oracle or shrink" 2>&1 | tail -3
+  NDDWT_CASC=$v timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_shrink.py -m gpu -x -q -k "${KSEL:-1d or cfg2 or batched or golden or parity_vs_oracle or shrink}" 2>&1 | tail -3
 done
 for v in $BV; do
   NDDWT_CASC=$v timeout 200 python bench.py --workload cfg2 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | python -c "
