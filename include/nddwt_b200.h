@@ -133,12 +133,19 @@ NDDWT_API int nddwt_dec(nddwt_plan *plan, const void *x_dev, void *coeffs_dev, i
 NDDWT_API int nddwt_shrink(nddwt_plan *plan, void *coeffs_dev, int level, void *stream);
 
 /* x = rec(y)          -- replaces nd_dwt_rec / nd_dwt_rec_1level (mex/nddwt.c:142-186,242-292).
- * Unlike the reference (nddwt.c:163,264-265) the coefficient stack is never modified. */
+ * Unlike the reference (nddwt.c:163,264-265) the coefficient stack is never modified.
+ * nddwt_dec / nddwt_rec / nddwt_shrink only launch kernels on `stream` once the plan's scratch exists (after the
+ * first call of that kind): no allocation, no synchronisation, no host round trip -- they can be captured into a
+ * CUDA graph and replayed (tests/test_gpu_parity.py::test_cuda_graph_capture_and_replay). */
 NDDWT_API int nddwt_rec(nddwt_plan *plan, const void *coeffs_dev, void *x_dev, int level, void *stream);
 
 /* Same two calls with HOST buffers: the shape of nd_dwt_mex(x, f, dir, level, pres_l2)
  * (mex/nd_dwt_mex.c:8-153) for host mxArrays.  Copies in, runs the kernels, copies out;
- * synchronous.  Host memory may be pageable or pinned. */
+ * synchronous.  Host memory may be pageable or pinned.
+ * 2-D ... 4-D arrays with two or more levels are LEVEL-STREAMED: the device holds x, the approximation
+ * ping-pong and two buffers of 2^d - 1 detail bands (not the whole coefficient stack), and the bands of
+ * one level cross PCIe while the next level computes -- (3 + 2 (2^d - 1)) N e of device memory (+ 2 N e of
+ * scratch in 4-D) instead of (3 + nb) N e. */
 NDDWT_API int nddwt_dec_host(nddwt_plan *plan, const void *x_host, void *coeffs_host, int level);
 NDDWT_API int nddwt_rec_host(nddwt_plan *plan, const void *coeffs_host, void *x_host, int level);
 

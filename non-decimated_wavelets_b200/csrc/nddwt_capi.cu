@@ -225,6 +225,11 @@ int nddwt_plan_destroy(nddwt_plan *p)
     if (p->host_x) cudaFree(p->host_x);
     if (p->host_c) cudaFree(p->host_c);
     if (p->host_stream) cudaStreamDestroy(p->host_stream);
+    if (p->host_copy) cudaStreamDestroy(p->host_copy);
+    for (int i = 0; i < 2; ++i) {
+        if (p->host_ev_k[i]) cudaEventDestroy(p->host_ev_k[i]);
+        if (p->host_ev_c[i]) cudaEventDestroy(p->host_ev_c[i]);
+    }
     for (size_t i = 0; i < p->timed.size(); ++i) { cudaEventDestroy(p->timed[i].e0); cudaEventDestroy(p->timed[i].e1); }
     for (size_t i = 0; i < p->event_pool.size(); ++i) cudaEventDestroy(p->event_pool[i]);
     delete p;
@@ -427,18 +432,118 @@ int nddwt_rec(nddwt_plan *p, const void *coeffs_dev, void *x_dev, int level, voi
     return 0;
 }
 
+// Host-pointer entry points.  `streamed`: the device holds x, the approximation ping-pong and TWO level buffers of
+// 2^d - 1 detail bands; whole stack otherwise (1-D: the cascade kernel wants the stack; one level: nothing to stream).
+static bool host_streamed(const nddwt_plan *p, int level) { return p->ndims >= 2 && level >= 2; }
+
 static int ensure_host_staging(nddwt_plan *p, int level)
 {
     NDDWT_CUDA(cudaSetDevice(p->device));
     const size_t band_bytes = (size_t)p->numel * p->esize;
-    const size_t need = band_bytes * (size_t)nddwt_num_bands(p->ndims, level);
+    const size_t nd = (size_t)1 << p->ndims;
+    const size_t need = host_streamed(p, level) ? 2 * (nd - 1) * band_bytes
+                                                : band_bytes * (size_t)nddwt_num_bands(p->ndims, level);
     if (!p->host_stream) NDDWT_CUDA(cudaStreamCreateWithFlags(&p->host_stream, cudaStreamNonBlocking));
+    if (!p->host_copy) NDDWT_CUDA(cudaStreamCreateWithFlags(&p->host_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        if (!p->host_ev_k[i]) NDDWT_CUDA(cudaEventCreateWithFlags(&p->host_ev_k[i], cudaEventDisableTiming));
+        if (!p->host_ev_c[i]) NDDWT_CUDA(cudaEventCreateWithFlags(&p->host_ev_c[i], cudaEventDisableTiming));
+    }
     if (!p->host_x) NDDWT_CUDA(cudaMalloc(&p->host_x, band_bytes));
     if (p->host_c_bytes < need) {
         if (p->host_c) { cudaFree(p->host_c); p->host_c = nullptr; p->host_c_bytes = 0; }
         NDDWT_CUDA(cudaMalloc(&p->host_c, need));
         p->host_c_bytes = need;
     }
+    return 0;
+}
+
+// Level-streamed analysis: level j writes its detail bands into level buffer j & 1; they leave for their (contiguous)
+// slots of the host stack on the copy stream while level j + 1 computes into the other buffer.  Device memory:
+// (1 + 2 (2^d - 1) + 2) N e instead of (1 + nb + 2) N e -- BASELINE configs[3] (46 bands of 4.3 GB) fits one 180 GB
+// GPU this way (35 N e = 150 GB), which the whole-stack form (197.6 GB) does not.
+static int dec_host_streamed(nddwt_plan *p, const void *x_host, void *coeffs_host, int level)
+{
+    const size_t band_bytes = (size_t)p->numel * p->esize;
+    const int nd = 1 << p->ndims;
+    const size_t lvl_bytes = (size_t)(nd - 1) * band_bytes;
+    cudaStream_t ks = p->host_stream, cs = p->host_copy;
+    char *hc = reinterpret_cast<char *>(coeffs_host);
+    NDDWT_CUDA(cudaMemcpyAsync(p->host_x, x_host, band_bytes, cudaMemcpyHostToDevice, ks));
+    const void *a_in = p->host_x;
+    LevelIO io;
+    for (int j = 1; j <= level; ++j) {
+        const int w = j & 1;
+        char *lvl = reinterpret_cast<char *>(p->host_c) + (size_t)w * lvl_bytes;
+        int rc = ensure_approx(p, w);
+        if (rc) return rc;
+        void *bands[1 << NDDWT_MAX_DIMS];
+        bands[0] = p->approx[w];
+        for (int b = 1; b < nd; ++b) bands[b] = lvl + (size_t)(b - 1) * band_bytes;
+        if (j > 2) NDDWT_CUDA(cudaStreamWaitEvent(ks, p->host_ev_c[w], 0));   // level j - 2 has left this buffer
+        p->cur_level = j;
+        rc = dec_level(p, p->dil[j - 1], a_in, io, bands, ks);
+        if (rc) return rc;
+        NDDWT_CUDA(cudaEventRecord(p->host_ev_k[w], ks));
+        NDDWT_CUDA(cudaStreamWaitEvent(cs, p->host_ev_k[w], 0));
+        // bands of level j live in slots (nd-1)(level-j)+1 .. +nd-1 (mex/nddwt.c:209-210,226): one contiguous block
+        const size_t start = (size_t)(nd - 1) * (size_t)(level - j);
+        NDDWT_CUDA(cudaMemcpyAsync(hc + (start + 1) * band_bytes, lvl, lvl_bytes, cudaMemcpyDeviceToHost, cs));
+        if (j == level) NDDWT_CUDA(cudaMemcpyAsync(hc, p->approx[w], band_bytes, cudaMemcpyDeviceToHost, cs));
+        NDDWT_CUDA(cudaEventRecord(p->host_ev_c[w], cs));
+        a_in = bands[0];
+    }
+    NDDWT_CUDA(cudaStreamSynchronize(cs));
+    NDDWT_CUDA(cudaStreamSynchronize(ks));
+    return 0;
+}
+
+// Level-streamed synthesis: the detail bands of level j - 1 arrive in the other level buffer while level j computes.
+static int rec_host_streamed(nddwt_plan *p, const void *coeffs_host, void *x_host, int level)
+{
+    const size_t band_bytes = (size_t)p->numel * p->esize;
+    const int nd = 1 << p->ndims;
+    const size_t lvl_bytes = (size_t)(nd - 1) * band_bytes;
+    cudaStream_t ks = p->host_stream, cs = p->host_copy;
+    const char *hc = reinterpret_cast<const char *>(coeffs_host);
+    int rc = ensure_approx(p, 0);
+    if (!rc) rc = ensure_approx(p, 1);
+    if (rc) return rc;
+    // a_J goes where level J + 1 would have written it
+    void *a = p->approx[(level + 1) & 1];
+    NDDWT_CUDA(cudaMemcpyAsync(a, hc, band_bytes, cudaMemcpyHostToDevice, cs));
+    for (int j = level; j >= 1; --j) {
+        const int w = j & 1;
+        char *lvl = reinterpret_cast<char *>(p->host_c) + (size_t)w * lvl_bytes;
+        if (j == level) {
+            const size_t start = (size_t)(nd - 1) * (size_t)(level - j);
+            NDDWT_CUDA(cudaMemcpyAsync(lvl, hc + (start + 1) * band_bytes, lvl_bytes, cudaMemcpyHostToDevice, cs));
+            NDDWT_CUDA(cudaEventRecord(p->host_ev_c[w], cs));
+        }
+        if (j > 1) {   // prefetch level j - 1 into the other buffer (level j + 1 read it last)
+            const int wn = (j - 1) & 1;
+            char *nxt = reinterpret_cast<char *>(p->host_c) + (size_t)wn * lvl_bytes;
+            if (j < level) NDDWT_CUDA(cudaStreamWaitEvent(cs, p->host_ev_k[wn], 0));
+            const size_t start = (size_t)(nd - 1) * (size_t)(level - (j - 1));
+            NDDWT_CUDA(cudaMemcpyAsync(nxt, hc + (start + 1) * band_bytes, lvl_bytes, cudaMemcpyHostToDevice, cs));
+            NDDWT_CUDA(cudaEventRecord(p->host_ev_c[wn], cs));
+        }
+        // level j: its details (and, for j == level, a_J: same stream, earlier) have landed -- host_ev_c[w] was
+        // recorded one iteration earlier, or just above for j == level
+        NDDWT_CUDA(cudaStreamWaitEvent(ks, p->host_ev_c[w], 0));
+        const void *bands[1 << NDDWT_MAX_DIMS];
+        bands[0] = a;
+        for (int b = 1; b < nd; ++b) bands[b] = lvl + (size_t)(b - 1) * band_bytes;
+        void *out = (j == 1) ? p->host_x : p->approx[w];
+        p->cur_level = j;
+        rc = rec_level(p, p->dil[j - 1], bands, out, ks);
+        if (rc) return rc;
+        NDDWT_CUDA(cudaEventRecord(p->host_ev_k[w], ks));
+        a = out;
+    }
+    NDDWT_CUDA(cudaMemcpyAsync(x_host, p->host_x, band_bytes, cudaMemcpyDeviceToHost, ks));
+    NDDWT_CUDA(cudaStreamSynchronize(ks));
+    NDDWT_CUDA(cudaStreamSynchronize(cs));
     return 0;
 }
 
@@ -449,6 +554,7 @@ int nddwt_dec_host(nddwt_plan *p, const void *x_host, void *coeffs_host, int lev
     if (!x_host || !coeffs_host) { set_error("null host pointer"); return NDDWT_ERR_ARG; }
     rc = ensure_host_staging(p, level);
     if (rc) return rc;
+    if (host_streamed(p, level)) return dec_host_streamed(p, x_host, coeffs_host, level);
     const size_t band_bytes = (size_t)p->numel * p->esize;
     const size_t nb = (size_t)nddwt_num_bands(p->ndims, level);
     NDDWT_CUDA(cudaMemcpyAsync(p->host_x, x_host, band_bytes, cudaMemcpyHostToDevice, p->host_stream));
@@ -466,6 +572,7 @@ int nddwt_rec_host(nddwt_plan *p, const void *coeffs_host, void *x_host, int lev
     if (!x_host || !coeffs_host) { set_error("null host pointer"); return NDDWT_ERR_ARG; }
     rc = ensure_host_staging(p, level);
     if (rc) return rc;
+    if (host_streamed(p, level)) return rec_host_streamed(p, coeffs_host, x_host, level);
     const size_t band_bytes = (size_t)p->numel * p->esize;
     const size_t nb = (size_t)nddwt_num_bands(p->ndims, level);
     NDDWT_CUDA(cudaMemcpyAsync(p->host_c, coeffs_host, band_bytes * nb, cudaMemcpyHostToDevice, p->host_stream));

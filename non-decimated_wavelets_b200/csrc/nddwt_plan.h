@@ -47,6 +47,11 @@ struct nddwt_plan {
     void *host_c = nullptr;
     size_t host_c_bytes = 0;
     cudaStream_t host_stream = nullptr;
+    // level-streamed host transforms (2-D ... 4-D, level >= 2): host_c then holds TWO level buffers of 2^d - 1 detail
+    // bands instead of the whole stack; the copies run on host_copy, ordered against the kernels by these events
+    cudaStream_t host_copy = nullptr;
+    cudaEvent_t host_ev_k[2] = {nullptr, nullptr};   // kernels of the level using level buffer i are done
+    cudaEvent_t host_ev_c[2] = {nullptr, nullptr};   // copy out of / into level buffer i is done
 
     // optional per-kernel CUDA-event timing (nddwt_plan_profile): event pairs recorded on the launch
     // stream around every kernel, grouped by kind

@@ -217,6 +217,29 @@ def test_cuda_graph_capture_and_replay(sizes, wn, level):
     assert orc.rel_l2(nd.to_host(xr), x2) <= 1e-5
 
 
+@pytest.mark.parametrize("sizes,wn,levels", [((96, 80), ["db2", "db4"], (3, 2, 4)), ((48, 40, 24), "db4", (2, 3)),
+                                             ((32, 24, 16, 12), "db4", (3, 2)), ((40, 33, 20), ["db1", "db3", "db9"], (2, 3))])
+@pytest.mark.parametrize("dtype", ["complex64", "float64"])
+def test_host_entry_points_stream_levels(sizes, wn, levels, dtype):
+    """nddwt_dec_host / nddwt_rec_host on 2-D ... 4-D arrays with two or more levels hold two LEVEL buffers on the device
+    (not the whole coefficient stack) and move the bands of one level over PCIe while the next level computes: the
+    result equals the device-pointer path and the oracle, across repeated calls and changing level counts on one plan."""
+    prec = _prec(dtype)
+    x = orc.synth(sizes, dtype, 91)
+    host = _obj(sizes, wn, 0, prec, compute="mex")
+    dev = _obj(sizes, wn, 0, prec, compute="gpu")
+    for level in levels:
+        for rep in range(2):
+            y = host.dec(x, level)
+            yd = nd.to_host(dev.dec(nd.to_device(x), level))
+            assert np.array_equal(y, yd)                      # same kernels, same order: bit-identical
+            yo = orc.dec_direct(x.astype(np.complex128 if np.iscomplexobj(x) else np.float64), wn, level)
+            assert orc.rel_l2(y, yo) <= TOL[prec]
+            c = orc.synth(y.shape, dtype, 92 + rep)
+            assert np.array_equal(host.rec(c), nd.to_host(dev.rec(nd.to_device(c))))
+            assert orc.rel_l2(host.rec(y), x) <= TOL[prec]
+
+
 def test_nd_dwt_mex_entry():
     x = orc.synth((32, 20), np.complex128, 1)
     f = nd.FilterSpec(["db2", "db3"], [32, 20])
