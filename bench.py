@@ -445,7 +445,7 @@ def main():
         hy_np = hy.numpy().T
         hobj = cls(wname, list(sizes), "precision", prec, "compute", "mex")
         hobj.set_kernel_mode(args.kernel_mode)
-        hx2 = torch.empty_like(hx)
+        hx2 = torch.empty(tuple(reversed(full)), dtype=x.dtype, pin_memory=True)   # (empty_like would not be pinned)
         hx2_np = hx2.numpy().T
         for _ in range(1 if (1 + nb) * nvox * esize > 8e9 else 2):
             hobj.dec(hx_np, level, out=hy_np)
