@@ -460,7 +460,8 @@ def main():
         e2e = {"value": nvox / t_e2e / 1e6, "unit": "Mvoxels/s",
                "h2d_bytes_per_step": (1 + nb) * nvox * esize, "d2h_bytes_per_step": (1 + nb) * nvox * esize,
                "ms_per_step": t_e2e * 1e3, "pr_rel_err": e2e_err,
-               "api": "nd_dwt_ND(...,'compute','mex').dec/rec -> nddwt_dec_host/nddwt_rec_host, pinned host arrays"}
+               "api": "nd_dwt_ND(...,'compute','mex').dec/rec -> nddwt_dec_host/nddwt_rec_host (level-streamed: one level's bands "
+                      "cross PCIe while the next level computes), pinned host arrays"}
         # for context (NOT the e2e value): the same pair in the reference's device-resident mode ('compute','gpu'), where
         # only x crosses PCIe each step and the coefficient stack stays in HBM -- x from pinned host memory, obj.dec,
         # obj.rec, result back to pinned host memory
