@@ -462,7 +462,7 @@ static int ensure_host_staging(nddwt_plan *p, int level)
 // slots of the host stack on the copy stream while level j + 1 computes into the other buffer.  Device memory:
 // (1 + 2 (2^d - 1) + 2) N e instead of (1 + nb + 2) N e -- BASELINE configs[3] (46 bands of 4.3 GB) fits one 180 GB
 // GPU this way (35 N e = 150 GB), which the whole-stack form (197.6 GB) does not.
-static int dec_host_streamed(nddwt_plan *p, const void *x_host, void *coeffs_host, int level)
+static int dec_host_streamed_issue(nddwt_plan *p, const void *x_host, void *coeffs_host, int level)
 {
     const size_t band_bytes = (size_t)p->numel * p->esize;
     const int nd = 1 << p->ndims;
@@ -493,13 +493,26 @@ static int dec_host_streamed(nddwt_plan *p, const void *x_host, void *coeffs_hos
         NDDWT_CUDA(cudaEventRecord(p->host_ev_c[w], cs));
         a_in = bands[0];
     }
-    NDDWT_CUDA(cudaStreamSynchronize(cs));
-    NDDWT_CUDA(cudaStreamSynchronize(ks));
     return 0;
 }
 
+// both streams are drained whatever happened: no copy may still be writing into the caller's arrays after the return
+static int host_streams_drain(nddwt_plan *p, int rc)
+{
+    const cudaError_t e1 = cudaStreamSynchronize(p->host_copy), e2 = cudaStreamSynchronize(p->host_stream);
+    if (rc) return rc;
+    if (e1 != cudaSuccess) return cuda_fail(e1, "cudaStreamSynchronize(copy stream)");
+    if (e2 != cudaSuccess) return cuda_fail(e2, "cudaStreamSynchronize(kernel stream)");
+    return 0;
+}
+
+static int dec_host_streamed(nddwt_plan *p, const void *x_host, void *coeffs_host, int level)
+{
+    return host_streams_drain(p, dec_host_streamed_issue(p, x_host, coeffs_host, level));
+}
+
 // Level-streamed synthesis: the detail bands of level j - 1 arrive in the other level buffer while level j computes.
-static int rec_host_streamed(nddwt_plan *p, const void *coeffs_host, void *x_host, int level)
+static int rec_host_streamed_issue(nddwt_plan *p, const void *coeffs_host, void *x_host, int level)
 {
     const size_t band_bytes = (size_t)p->numel * p->esize;
     const int nd = 1 << p->ndims;
@@ -542,9 +555,12 @@ static int rec_host_streamed(nddwt_plan *p, const void *coeffs_host, void *x_hos
         a = out;
     }
     NDDWT_CUDA(cudaMemcpyAsync(x_host, p->host_x, band_bytes, cudaMemcpyDeviceToHost, ks));
-    NDDWT_CUDA(cudaStreamSynchronize(ks));
-    NDDWT_CUDA(cudaStreamSynchronize(cs));
     return 0;
+}
+
+static int rec_host_streamed(nddwt_plan *p, const void *coeffs_host, void *x_host, int level)
+{
+    return host_streams_drain(p, rec_host_streamed_issue(p, coeffs_host, x_host, level));
 }
 
 int nddwt_dec_host(nddwt_plan *p, const void *x_host, void *coeffs_host, int level)
