@@ -134,17 +134,30 @@ def test_multi_gpu_options_and_export_blob_size():
 
 def test_header_is_plain_c_and_every_entry_point_links(tmp_path):
     """The drop-in boundary is a C ABI: include/nddwt_b200.h compiles as C99 (no C++-isms, no torch types) and a C
-    program that takes the address of every declared entry point links against libnddwt_b200.so."""
+    program that takes the address of every declared entry point links against libnddwt_b200.so; the entry points that
+    need no device (wave_filters, num_bands, the error channel) answer from plain C exactly as through ctypes."""
     import subprocess
     hdr = open(os.path.join(ROOT, "include", "nddwt_b200.h")).read()
     names = sorted(set(re.findall(r"NDDWT_API[^;(]*?\b(nddwt_\w+)\s*\(", hdr)))
     src = tmp_path / "abi_check.c"
     src.write_text('#include "nddwt_b200.h"\n#include <stdio.h>\ntypedef void (*fn_t)(void);\nint main(void) {\n  fn_t fn[] = {\n'
                    + "".join("    (fn_t)%s,\n" % n for n in names)
-                   + '  };\n  printf("%d entry points, %s\\n", (int)(sizeof fn / sizeof fn[0]), nddwt_version());\n  return 0;\n}\n')
+                   + '  };\n  double lo[20], hi[20]; int len = 0, rc, k;\n'
+                     '  printf("%d entry points, %s\\n", (int)(sizeof fn / sizeof fn[0]), nddwt_version());\n'
+                     '  rc = nddwt_wave_filters("db4", lo, hi, &len);\n  printf("rc %d len %d\\n", rc, len);\n'
+                     '  for (k = 0; k < len; ++k) printf("%.17g %.17g\\n", lo[k], hi[k]);\n'
+                     '  printf("nb %d\\n", (int)nddwt_num_bands(4, 3));\n'
+                     '  rc = nddwt_wave_filters("db11", lo, hi, &len);\n  printf("rc %d msg %s\\n", rc, nddwt_last_error());\n'
+                     '  return 0;\n}\n')
     libdir = os.path.dirname(nd.LIB_PATH)
     exe = tmp_path / "abi_check"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
                            str(src), "-o", str(exe), "-L", libdir, "-lnddwt_b200", "-Wl,-rpath," + libdir])
-    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
-    assert out.startswith("%d entry points" % len(names)) and "sm_100a" in out
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert out[0].startswith("%d entry points" % len(names)) and "sm_100a" in out[0]
+    assert out[1] == "rc 0 len 8"
+    lo, hi = orc.wave_filters("db4")
+    got = np.array([[float(v) for v in ln.split()] for ln in out[2:10]])
+    assert np.array_equal(got[:, 0], lo) and np.array_equal(got[:, 1], hi)      # taps to the last bit (wave_filters.m:21-156)
+    assert out[10] == "nb 46"                                                   # BASELINE configs[3]: 1 + 3 (2^4 - 1)
+    assert out[11].startswith("rc -2") and "Unknown Wavelet Name" in out[11]
