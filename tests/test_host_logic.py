@@ -161,3 +161,42 @@ def test_header_is_plain_c_and_every_entry_point_links(tmp_path):
     assert np.array_equal(got[:, 0], lo) and np.array_equal(got[:, 1], hi)      # taps to the last bit (wave_filters.m:21-156)
     assert out[10] == "nb 46"                                                   # BASELINE configs[3]: 1 + 3 (2^4 - 1)
     assert out[11].startswith("rc -2") and "Unknown Wavelet Name" in out[11]
+
+
+def test_m_files_call_the_gateway_the_way_it_is_written():
+    """The .m classes cannot be executed here (no MATLAB), so at least their calls into nd_dwt_mex are checked against
+    the gateway source: every string command they use exists there and is called with an argument count it accepts,
+    the five-argument transform call has the reference's shape (mex/nd_dwt_mex.c:8-9), and the option keys handled by
+    nddwt_b200_setup.m are the ones the Python mirror (api.py) handles."""
+    mdir = os.path.join(ROOT, "non-decimated_wavelets_b200", "matlab")
+    gw = open(os.path.join(mdir, "nd_dwt_mex.cpp")).read()
+    accepts = {}
+    for cmd, op, n in re.findall(r'strcmp\(cmd, "(\w+)"\) == 0(?: && nrhs (==|>=) (\d+))?', gw):
+        accepts[cmd] = (op or ">=", int(n) if n else 1)
+    assert set(accepts) == {"taps", "plan", "shrink", "dilations", "release"}
+    calls = []
+    for fn in sorted(os.listdir(mdir)):
+        if not fn.endswith(".m"):
+            continue
+        for line in open(os.path.join(mdir, fn)):
+            code = line.split("%")[0]
+            for m in re.finditer(r"nd_dwt_mex\(([^;]*)\)", code):
+                args = [a.strip() for a in re.split(r",(?![^\[\]]*\])", m.group(1).rstrip(" ,.)"))]
+                calls.append((fn, args))
+    assert len(calls) >= 6
+    for fn, args in calls:
+        if args[0].startswith("'"):
+            cmd = args[0].strip("'")
+            assert cmd in accepts, (fn, cmd)
+            op, n = accepts[cmd]
+            assert (len(args) == n) if op == "==" else (len(args) >= n), (fn, args)
+        else:
+            assert len(args) == 5, (fn, args)          # y = nd_dwt_mex(x, f, dir, level, pres_l2_norm)
+    setup = open(os.path.join(mdir, "nddwt_b200_setup.m")).read()
+    m_keys = set(re.findall(r"strcmp\(key, '(\w+)'\)", setup))
+    api = open(os.path.join(ROOT, "non-decimated_wavelets_b200", "api.py")).read()
+    for key in m_keys:
+        assert '"%s"' % key in api, key
+    assert {"pres_l2_norm", "compute", "precision"} <= m_keys
+    for text in ("ingoring!", "of Data is shorter than the wavelet filter being used"):     # the reference's own texts
+        assert text in setup and text in api
