@@ -79,7 +79,11 @@ NDDWT_API int nddwt_plan_create(nddwt_plan **plan, int ndims, const int64_t *dim
 NDDWT_API int nddwt_plan_destroy(nddwt_plan *plan);
 
 /* Opt-in a-trous mode: dilation of the taps at level j (1-based) is dil[j-1].  Default (and
- * reference parity, nd_dwt_2D.m:183 / nddwt.c:214-228): 1 at every level. */
+ * reference parity, nd_dwt_2D.m:183 / nddwt.c:214-228): 1 at every level.
+ * A dilated level runs the same fused kernels with its taps stretched about their centre (an L-tap filter at
+ * dilation s = an L s-tap filter with zeros in between): 3-D / 4-D tile kernels while L s <= 8 (Haar at 1, 2, 4;
+ * db2 at 1, 2), 2-D kernels and the hybrid level while L s <= 20, the generic separable kernels beyond that, for
+ * slabs, and in the 1-D cascade. */
 NDDWT_API int nddwt_plan_set_dilations(nddwt_plan *plan, const int *dil, int nlevels);
 
 /* Extension (the reference has no batch API): the arrays carry one extra trailing

@@ -1473,8 +1473,8 @@ static FusedTaps<T, L> make_taps(const nddwt_plan *p, bool rec)
     for (int d = 0; d < 3; ++d)
         for (int k = 0; k < L; ++k) {
             const int dd = d < p->ndims ? d : 0;
-            t.lo[d][k] = mk_tap(typename TapOf<T>::type(), padded_tap(src.d[dd].lo, p->L[dd], L, k));
-            t.hi[d][k] = mk_tap(typename TapOf<T>::type(), padded_tap(src.d[dd].hi, p->L[dd], L, k));
+            t.lo[d][k] = mk_tap(typename TapOf<T>::type(), padded_tap(src.d[dd].lo, p->L[dd], L, k, p->cur_dil));
+            t.hi[d][k] = mk_tap(typename TapOf<T>::type(), padded_tap(src.d[dd].hi, p->L[dd], L, k, p->cur_dil));
         }
     return t;
 }
@@ -1900,11 +1900,11 @@ static bool uniform_taps(const nddwt_plan *p) { return plan_uniform_taps(p); }
 // db4 (the register ring); slabs (halo planes counted for the TRUE filter of the last dim) need uniform taps
 static int fused_L(const nddwt_plan *p, bool slab)
 {
-    if (slab && !plan_uniform_taps(p)) return 0;
-    const int L = plan_max_taps(p);
-    if (!plan_uniform_taps(p))
+    if (slab && (!plan_uniform_taps(p) || p->cur_dil != 1)) return 0;
+    const int L = plan_max_taps(p);            // includes the dilation of the level in flight (stretched taps)
+    if (!plan_uniform_taps(p) || p->cur_dil != 1)
         for (int i = 0; i < p->ndims; ++i)
-            if (p->dims[i] < L) return 0;      // a padded filter longer than the dimension: generic kernels
+            if (p->dims[i] < L) return 0;      // a padded / stretched filter longer than the dimension: generic kernels
     return (L == 2 || L == 4 || L == 6 || L == 8) ? L : 0;
 }
 // ------------------------------- 4-D path ---------------------------------------------------
@@ -1915,8 +1915,8 @@ static LastTaps<T, L> make_last_taps(const nddwt_plan *p, bool rec)
     const AllTaps<double> &src = rec ? p->rec_d : p->dec_d;
     const int d = p->ndims - 1;
     for (int k = 0; k < L; ++k) {
-        t.lo[k] = mk_tap(typename TapOf<T>::type(), padded_tap(src.d[d].lo, p->L[d], L, k));
-        t.hi[k] = mk_tap(typename TapOf<T>::type(), padded_tap(src.d[d].hi, p->L[d], L, k));
+        t.lo[k] = mk_tap(typename TapOf<T>::type(), padded_tap(src.d[d].lo, p->L[d], L, k, p->cur_dil));
+        t.hi[k] = mk_tap(typename TapOf<T>::type(), padded_tap(src.d[d].hi, p->L[d], L, k, p->cur_dil));
     }
     return t;
 }
@@ -2283,8 +2283,10 @@ int fused_rec_stage2(nddwt_plan *p, int dil, const void *u_lo, const void *u_hi,
 int fused_dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io, void *const *out_bands,
                     cudaStream_t s)
 {
+    if (dil < 1 || dil > 4) return 1;
+    DilScope ds(p, dil);                       // a-trous levels: the same kernels with stretched taps (nddwt_plan.h)
     const int FL = fused_L(p, io.halo_lo != nullptr || io.halo_hi != nullptr);
-    if (dil != 1 || FL == 0 || !dec_rows_ok(p)) return 1;
+    if (FL == 0 || !dec_rows_ok(p)) return 1;
     if (p->ndims == 3) {
         if (!fused_ranges_ok(p)) return 1;
         if (p->dims[0] < FL || p->dims[1] < FL) return 1;
@@ -2303,8 +2305,10 @@ int fused_dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io,
 
 int fused_rec_level(nddwt_plan *p, int dil, const void *const *in_bands, void *a_out, cudaStream_t s)
 {
+    if (dil < 1 || dil > 4) return 1;
+    DilScope ds(p, dil);
     const int FL = fused_L(p, false);
-    if (dil != 1 || FL == 0) return 1;
+    if (FL == 0) return 1;
     if (p->ndims == 3) {
         if (!fused_ranges_ok(p)) return 1;
         if (p->dims[0] < FL || p->dims[1] < FL) return 1;

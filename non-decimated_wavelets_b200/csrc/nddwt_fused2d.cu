@@ -137,8 +137,8 @@ static Taps2<T, L> make_taps2(const nddwt_plan *p, bool rec, int band0 = 0)
     const AllTaps<double> &src = rec ? p->rec_d : p->dec_d;
     for (int d = 0; d < 2; ++d)
         for (int k = 0; k < L; ++k) {
-            t.lo[d][k] = (R)padded_tap(src.d[d].lo, p->L[d], L, k);     // mixed wavelets: the shorter filter is zero-padded
-            t.hi[d][k] = (R)padded_tap(src.d[d].hi, p->L[d], L, k);
+            t.lo[d][k] = (R)padded_tap(src.d[d].lo, p->L[d], L, k, p->cur_dil);     // mixed wavelets: zero-padded; a-trous levels: stretched
+            t.hi[d][k] = (R)padded_tap(src.d[d].hi, p->L[d], L, k, p->cur_dil);
         }
     const int j = p->cur_level >= 1 && p->cur_level <= NDDWT_MAX_LEVELS ? p->cur_level : 1;
     for (int b = 0; b < 4; ++b) t.thr[b] = (R)((!rec && p->shrink_mode) ? p->shrink_thr[j - 1][band0 + b] : 0.0);
@@ -211,7 +211,7 @@ static int launch_rec2(nddwt_plan *p, const void *const *in_bands, void *a_out, 
         default: return 1;                                 \
     }
 
-static int taps2d(const nddwt_plan *p) { return p->L[0] > p->L[1] ? p->L[0] : p->L[1]; }   // dims 1, 2 only
+static int taps2d(const nddwt_plan *p) { return (p->L[0] > p->L[1] ? p->L[0] : p->L[1]) * p->cur_dil; }   // dims 1, 2 only; stretched on a-trous levels
 
 template <typename T>
 static int dispatch_dec2(nddwt_plan *p, const void *a_in, void *const *out_bands, cudaStream_t s, int64_t planes = 1,
@@ -227,7 +227,7 @@ static int dispatch_rec2(nddwt_plan *p, const void *const *in_bands, void *a_out
 
 static bool ok2d_geometry(const nddwt_plan *p)
 {
-    if (p->ndims < 2) return false;
+    if (p->ndims < 2 || taps2d(p) > 20) return false;
     if (p->dims[0] < taps2d(p) || p->dims[1] < taps2d(p)) return false;
     if (p->dims[0] > 0x7fffffff - 64 || p->dims[1] > (int64_t)65535 * 16) return false;
     return p->dims[0] * p->dims[1] < ((int64_t)1 << 31);
@@ -262,7 +262,8 @@ int fused2d_rec_planes(nddwt_plan *p, const void *const *in_bands, void *a_out, 
 
 static bool ok2d(const nddwt_plan *p, int dil, const LevelIO *io)
 {
-    if (dil != 1 || p->ndims != 2 || p->batch != 1) return false;
+    if (dil != p->cur_dil || p->ndims != 2 || p->batch != 1) return false;
+    if (taps2d(p) > 20) return false;                          // stretched taps beyond the longest instantiation
     if (p->dims[0] < taps2d(p) || p->dims[1] < taps2d(p)) return false;
     if (io && (io->halo_lo || io->halo_hi)) return false;      // slabs of 2-D arrays use the generic kernels
     // launch geometry: dims are ints in the kernels, grid.y = ceil(n2 / 16) must stay <= 65535
@@ -273,6 +274,8 @@ static bool ok2d(const nddwt_plan *p, int dil, const LevelIO *io)
 int fused2d_dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &io, void *const *out_bands,
                       cudaStream_t s)
 {
+    if (dil < 1 || dil > 10) return 1;
+    DilScope ds(p, dil);
     if (!ok2d(p, dil, &io)) return 1;
     switch (p->dtype) {
         case NDDWT_F32: return dispatch_dec2<float>(p, a_in, out_bands, s);
@@ -285,6 +288,8 @@ int fused2d_dec_level(nddwt_plan *p, int dil, const void *a_in, const LevelIO &i
 
 int fused2d_rec_level(nddwt_plan *p, int dil, const void *const *in_bands, void *a_out, cudaStream_t s)
 {
+    if (dil < 1 || dil > 10) return 1;
+    DilScope ds(p, dil);
     if (!ok2d(p, dil, nullptr)) return 1;
     switch (p->dtype) {
         case NDDWT_F32: return dispatch_rec2<float>(p, in_bands, a_out, s);

@@ -171,8 +171,9 @@ static int dec_recurse(nddwt_plan *p, int k, int dil, const T *in, const LevelIO
     const T *hh = last ? reinterpret_cast<const T *>(io.halo_hi) : nullptr;
     // hybrid: dims 1 and 2 of every remaining plane in one fused 2-D launch (4 bands written once) instead of two more
     // generic passes with their intermediates; the outer dims were filtered by the passes above
-    if (k == 1 && dil == 1 && p->kernel_mode == 0 && !(last && (hl || hh))) {
+    if (k == 1 && dil >= 1 && dil <= 10 && p->kernel_mode == 0 && !(last && (hl || hh))) {
         const int64_t planes = p->numel / (p->dims[0] * p->dims[1]);
+        DilScope ds(p, dil);                   // a-trous levels: stretched taps in the 2-D kernels (nddwt_plan.h)
         const int rc = fused2d_dec_planes(p, in, out_bands + idx * 4, planes, idx * 4, s);
         if (rc <= 0) { p->hybrid_used = true; return rc; }
     }
@@ -194,8 +195,9 @@ static int dec_recurse(nddwt_plan *p, int k, int dil, const T *in, const LevelIO
 template <typename T>
 static int rec_recurse(nddwt_plan *p, int k, int dil, int idx, const void *const *bands, T *dst, cudaStream_t s)
 {
-    if (k == 2 && dil == 1 && p->kernel_mode == 0) {      // hybrid: dims 1, 2 by the fused 2-D kernels
+    if (k == 2 && dil >= 1 && dil <= 10 && p->kernel_mode == 0) {      // hybrid: dims 1, 2 by the fused 2-D kernels
         const int64_t planes = p->numel / (p->dims[0] * p->dims[1]);
+        DilScope ds(p, dil);
         const int rc = fused2d_rec_planes(p, bands + idx * 4, dst, planes, s);
         if (rc <= 0) { p->hybrid_used = true; return rc; }
     }

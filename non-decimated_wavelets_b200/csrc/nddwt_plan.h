@@ -36,6 +36,7 @@ struct nddwt_plan {
     int shrink_mode = 0;
     double shrink_thr[NDDWT_MAX_LEVELS][1 << NDDWT_MAX_DIMS];
     int cur_level = 1;         // level index of the level call in flight (selects the threshold row)
+    int cur_dil = 1;           // dilation of the level call in flight when it runs the fused kernels (taps stretched, see padded_tap)
     int rows_min_ctas = 118;   // full-row synthesis kernel needs at least this many CTAs (nddwt_plan_set_param)
 
     // device scratch owned by the plan (allocated on first use, reused across calls)
@@ -81,17 +82,29 @@ struct LevelIO {
 // Mixed wavelets in the fused kernels: every dimension runs with the LONGEST tap length of the plan; a shorter
 // filter is zero-padded symmetrically (m = (L - L_i)/2 zeros on each side), which leaves its phase L_i/2 and
 // therefore the result unchanged: sum_k g[k] x[n - k + L_i/2] == sum_k' g'[k'] x[n - k' + L/2].
+// A-trous levels (dilation s > 1) run the same kernels the same way: the taps are STRETCHED about their centre,
+// g'[(k - L_i/2) s + L/2] = g[k] and zero elsewhere, so that sum_k' g'[k'] x[n - (k' - L/2)] ==
+// sum_k g[k] x[n - (k - L_i/2) s] -- an effective filter of L_i s taps (Haar at dilations 1, 2, 4 = the 2-, 4- and 8-tap
+// instantiations of the tile kernels; up to 20 taps in the 2-D kernels).
 inline int plan_max_taps(const nddwt_plan *p)
 {
     int m = 0;
     for (int i = 0; i < p->ndims; ++i) m = p->L[i] > m ? p->L[i] : m;
-    return m;
+    return m * p->cur_dil;
 }
-inline double padded_tap(const double *taps, int Li, int L, int k)
+inline double padded_tap(const double *taps, int Li, int L, int k, int s = 1)
 {
-    const int m = (L - Li) / 2;
-    return (k >= m && k < m + Li) ? taps[k - m] : 0.0;
+    const int c = k - L / 2;                 // offset from the centre, in samples
+    if (c % s != 0) return 0.0;
+    const int kk = c / s + Li / 2;
+    return (kk >= 0 && kk < Li) ? taps[kk] : 0.0;
 }
+// sets the dilation of the level in flight for the duration of a fused-path attempt
+struct DilScope {
+    nddwt_plan *p;
+    DilScope(nddwt_plan *plan, int dil) : p(plan) { p->cur_dil = dil; }
+    ~DilScope() { p->cur_dil = 1; }
+};
 inline bool plan_uniform_taps(const nddwt_plan *p)
 {
     for (int i = 1; i < p->ndims; ++i)

@@ -385,6 +385,51 @@ def test_atrous_option_and_haar_multilevel():
     assert abs(np.linalg.norm(y3.ravel()) / np.linalg.norm(x3.ravel()) - 1) < 1e-11      # still a tight frame
 
 
+@pytest.mark.parametrize("sizes,wn,dil,dtype,paths", [
+    ((24, 20, 16, 16), "db1", [1, 2, 4], "complex64", [1, 1, 1]),      # a-trous Haar, 3 levels: 2-, 4-, 8-tap tile kernels
+    ((40, 36, 32), "db1", [1, 2, 4], "complex64", [1, 1, 1]),
+    ((40, 36, 32), "db2", [1, 2, 4], "float64", [1, 1, 2]),            # 16 stretched taps: dim 3 generic + fused 2-D planes
+    ((32, 24, 16, 16), "db2", [1, 2], "complex64", [1, 1]),
+    ((40, 36, 32), "db3", [1, 2], "complex128", [1, 2]),               # 12 stretched taps: hybrid
+    ((96, 80), "db4", [1, 2], "complex64", [1, 1]),                    # 2-D: 16 stretched taps
+    ((96, 80), "db5", [1, 2], "float32", [1, 1]),                      # 20 taps, the longest instantiation
+    ((96, 80), "db1", [1, 2, 4, 8], "complex128", [1, 1, 1, 1]),
+    ((96, 80), "db4", [1, 2, 4], "complex64", [1, 1, 0]),              # 32 taps: generic
+    ((131, 30, 20), ["db1", "db2", "db1"], [1, 2], "complex64", [1, 1]),   # mixed wavelets, odd rows, stretched
+])
+def test_atrous_levels_take_the_fused_kernels(sizes, wn, dil, dtype, paths):
+    """A-trous levels run the SAME fused kernels with their taps stretched about the centre (an L-tap
+    filter at dilation s is an L s-tap filter with zeros in between): Haar at dilations 1, 2, 4 -- the multi-level Haar the
+    reference's harr_nddwt_4D.m:175,222 cannot compute -- takes the 2-, 4- and 8-tap tile kernels; the 2-D kernels go up to
+    20 stretched taps; beyond that the level is hybrid (generic outer passes + fused 2-D planes) or generic.
+    Oracle: the closed-form restatement with the same dilations; kernel family per level from the plan."""
+    prec = _prec(dtype)
+    x = orc.synth(sizes, dtype, 61)
+    cplx = np.iscomplexobj(x)
+    a = _obj(sizes, wn, 1, prec, kernel_mode=0)
+    b = _obj(sizes, wn, 1, prec, kernel_mode=1)
+    a.set_dilations(dil)
+    b.set_dilations(dil)
+    level = len(dil)
+    ya = a.dec(x, level)
+    yo = orc.dec_direct(x.astype(np.complex128 if cplx else np.float64), wn, level, True, dilations=dil)
+    assert orc.rel_l2(ya, yo) <= TOL[prec]
+    assert orc.rel_l2(ya, b.dec(x, level)) <= 10 * TOL[prec]
+    assert orc.rel_l2(a.rec(ya), x) <= TOL[prec]
+    c = orc.synth(ya.shape, dtype, 62)
+    assert orc.rel_l2(a.rec(c), b.rec(c)) <= 10 * TOL[prec]             # adjoint on arbitrary coefficients
+    assert abs(np.linalg.norm(ya.ravel()) / np.linalg.norm(x.ravel()) - 1) < 1e3 * TOL[prec]   # still a tight frame
+    # kernel family of each level: run them one at a time (a one-level transform with that level's dilation)
+    pa = a._plan(cplx, 0)
+    for s_, want in zip(dil, paths):
+        a.set_dilations([s_])
+        a.dec(x, 1)
+        assert pa.last_path == want, (s_, pa.last_path, want)
+        y1 = a.dec(x, 1)
+        a.rec(y1)
+        assert pa.last_path == want, ("rec", s_, pa.last_path, want)
+
+
 def test_4d_full_size_properties_cfg5():
     """Size-independent properties at BASELINE configs[4]'s full size (192x192x64x48 complex single,
     db4, 3 levels; the bench.py N=1 workload): perfect reconstruction, linearity, energy."""
