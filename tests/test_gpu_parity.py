@@ -520,3 +520,54 @@ def test_full_row_synthesis_kernel(sizes, level, wn, dtype):
     assert orc.rel_l2(b.rec(c), orc.rec_direct(c.astype(wide), wn, True)) <= TOL[prec]
     assert orc.rel_l2(a.rec(c), g.rec(c)) <= (2e-6 if prec == "single" else 1e-13)
 
+
+
+def test_plain_c_caller_dec_rec(tmp_path):
+    """A C99 program (no C++, no Python, no torch) drives the library through include/nddwt_b200.h: plan, host-pointer dec
+    and rec of a 3-D complex-single array, perfect reconstruction, the band count, and an error return with its text --
+    what a C host application (or another language's FFI) sees."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "c_caller.c"
+    src.write_text(r'''
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include "nddwt_b200.h"
+int main(void)
+{
+    const int64_t dims[3] = {48, 40, 24};
+    const char *w[3] = {"db4", "db2", "db4"};
+    const int level = 2;
+    const int64_t n = dims[0] * dims[1] * dims[2], nb = nddwt_num_bands(3, level);
+    float *x = malloc(sizeof(float) * 2 * n), *xr = malloc(sizeof(float) * 2 * n), *y = malloc(sizeof(float) * 2 * n * nb);
+    nddwt_plan *p = NULL;
+    double num = 0.0, den = 0.0, e2 = 0.0;
+    int64_t i;
+    unsigned s = 12345u;
+    int rc;
+    for (i = 0; i < 2 * n; ++i) { s = s * 1664525u + 1013904223u; x[i] = (float)((double)(s >> 8) / 8388608.0 - 1.0); }
+    rc = nddwt_plan_create(&p, 3, dims, w, NDDWT_C64, 1, 0);
+    if (rc) { printf("plan rc %d %s\n", rc, nddwt_last_error()); return 1; }
+    rc = nddwt_dec_host(p, x, y, level);
+    if (rc) { printf("dec rc %d %s\n", rc, nddwt_last_error()); return 1; }
+    rc = nddwt_rec_host(p, y, xr, level);
+    if (rc) { printf("rec rc %d %s\n", rc, nddwt_last_error()); return 1; }
+    for (i = 0; i < 2 * n; ++i) { num += (double)(xr[i] - x[i]) * (xr[i] - x[i]); den += (double)x[i] * x[i]; }
+    for (i = 0; i < 2 * n * nb; ++i) e2 += (double)y[i] * y[i];
+    printf("bands %d pr %.3e energy %.6f\n", (int)nb, sqrt(num / den), sqrt(e2 / den));
+    rc = nddwt_dec_host(p, x, y, 99);
+    printf("bad level rc %d msg %s\n", rc, nddwt_last_error());
+    nddwt_plan_destroy(p);
+    free(x); free(xr); free(y);
+    return 0;
+}
+''')
+    libdir = os.path.dirname(nd.LIB_PATH)
+    exe = tmp_path / "c_caller"
+    subprocess.check_call(["gcc", "-std=c99", "-O1", "-Wall", "-Wextra", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-lnddwt_b200", "-lm", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+    f = out[0].split()
+    assert f[0] == "bands" and int(f[1]) == 15 and float(f[3]) <= 1e-5 and abs(float(f[5]) - 1.0) <= 1e-4     # pres_l2_norm: tight frame
+    assert out[1].startswith("bad level rc -1") and "level" in out[1]
